@@ -1,0 +1,19 @@
+"""CPU oracle for the GenPercept one-step hot path.  TEST INFRASTRUCTURE ONLY.
+
+Plain-PyTorch fp32 restatement of ``GenPerceptPipeline.single_infer``
+(/root/reference/genpercept/genpercept_pipeline.py:375-526) and of the third-party graphs it
+drives (diffusers 0.26-0.29 ``AutoencoderKL`` / ``UNet2DConditionModel`` with the
+stabilityai/stable-diffusion-2-1 configs, restated from SURVEY.md Appendix A because diffusers is
+not installed and is not vendored under /root/reference) plus the in-tree DPT head
+(/root/reference/genpercept/models/dpt_head.py).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this package; the product path (``genpercept_b200``) never does.
+
+PARITY STATUS: the reference holds no tests or golden tensors for this path, and
+its arithmetic lives in diffusers which cannot be imported here -> **parity unpinned** for the
+VAE/UNet graphs.  What *is* pinned (tests/test_oracle.py): the DPT head against the reference's own
+class (imported from /root/reference through a 2-symbol diffusers shim; fixtures committed under
+tests/golden/), the scheduler collapse against a literal restatement of ddim.py, parameter counts
+against the published model sizes, and the empty-text embedding fixture.
+"""
