@@ -1,0 +1,466 @@
+// Plan-time arena and op-list builder: turns layer-level calls (conv, attention, norms ...) into
+// fully parameterised kernel launches (tensor maps encoded once, at plan time).
+#include <algorithm>
+#include <cstring>
+
+#include "engine.h"
+
+namespace gp {
+
+// ------------------------------------------------------------------------------------ Arena
+size_t Arena::alloc(size_t bytes) {
+  bytes = (bytes + 1023) & ~size_t(1023);
+  if (bytes == 0) bytes = 1024;
+  for (size_t i = 0; i < blks_.size(); ++i) {
+    if (blks_[i].free && blks_[i].size >= bytes) {
+      if (blks_[i].size > bytes) {
+        Blk rest{blks_[i].off + bytes, blks_[i].size - bytes, true};
+        blks_[i].size = bytes;
+        blks_.insert(blks_.begin() + i + 1, rest);
+      }
+      blks_[i].free = false;
+      return blks_[i].off;
+    }
+  }
+  size_t off = blks_.empty() ? 0 : blks_.back().off + blks_.back().size;
+  if (!blks_.empty() && blks_.back().free) {   // grow the trailing free block
+    off = blks_.back().off;
+    blks_.back().size = bytes;
+    blks_.back().free = false;
+  } else {
+    blks_.push_back(Blk{off, bytes, false});
+  }
+  high_ = std::max(high_, off + bytes);
+  return off;
+}
+
+void Arena::release(size_t off) {
+  for (size_t i = 0; i < blks_.size(); ++i) {
+    if (blks_[i].off == off && !blks_[i].free) {
+      blks_[i].free = true;
+      if (i + 1 < blks_.size() && blks_[i + 1].free) {
+        blks_[i].size += blks_[i + 1].size;
+        blks_.erase(blks_.begin() + i + 1);
+      }
+      if (i > 0 && blks_[i - 1].free) {
+        blks_[i - 1].size += blks_[i].size;
+        blks_.erase(blks_.begin() + i);
+      }
+      return;
+    }
+  }
+  throw GpError(GP_ERR_STATE, "arena: release of unknown block");
+}
+
+// ------------------------------------------------------------------------------------ Builder
+T4 Builder::alloc(int N, int H, int W, int C) {
+  T4 t;
+  t.N = N; t.H = H; t.W = W; t.C = C;
+  t.off = (long long)arena_.alloc(t.bytes());
+  return t;
+}
+T4 Builder::external(const void* p, int N, int H, int W, int C) const {
+  T4 t;
+  t.N = N; t.H = H; t.W = W; t.C = C;
+  t.off = (long long)(reinterpret_cast<const uint8_t*>(p) - base_);
+  return t;
+}
+void Builder::release(const T4& t) { arena_.release((size_t)t.off); }
+
+void Builder::push(const std::string& name, int launches, double flops, double bytes,
+                   std::function<cudaError_t(cudaStream_t)> fn) {
+  Op o;
+  o.name = name;
+  o.stage = stage;
+  o.variant = variant;
+  o.launches = launches;
+  o.flops = flops;
+  o.bytes = bytes;
+  o.run = std::move(fn);
+  ops.push_back(std::move(o));
+}
+void Builder::custom(const std::string& name, int launches, double bytes, std::function<cudaError_t(cudaStream_t)> fn) {
+  if (measuring_) return;
+  push(name, launches, 0, bytes, std::move(fn));
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int choose_bn(int cout, int force) {
+  if (force) return force;
+  const int c16 = ceil_div(cout, 16) * 16;
+  if (c16 <= 256) return c16;
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (cout % bn == 0) return bn;
+  const int n = ceil_div(cout, 256);
+  return ceil_div(ceil_div(cout, n), 16) * 16;
+}
+// pick the TW x TH = 128 patch with the least padding waste (ties: wider rows)
+static void choose_tile(int gw, int gh, int* tw, int* th, int* shift) {
+  double best = 1e30;
+  for (int s = 7; s >= 0; --s) {
+    const int w = 1 << s, h = 128 >> s;
+    const double waste = (double)ceil_div(gw, w) * w * ceil_div(gh, h) * h / ((double)gw * gh);
+    if (waste < best - 1e-9) { best = waste; *tw = w; *th = h; *shift = s; }
+  }
+}
+
+static void check_cuda(cudaError_t e, const std::string& what) {
+  if (e != cudaSuccess) throw GpError(GP_ERR_CUDA, what + ": " + cudaGetErrorString(e));
+}
+static void finalize_or_throw(IgemmParams* p, const std::string& name) {
+  const char* err = igemm_finalize(p);
+  if (err) throw GpError(GP_ERR_INVALID, name + ": " + err);
+}
+
+void Builder::conv(const std::string& name, const ConvArgs& a) {
+  GP_REQUIRE(!a.srcs.empty() && a.w != nullptr, name + ": bad conv args");
+  const T4& s0 = a.srcs[0];
+  const int N = s0.N, H = s0.H, W = s0.W;
+  int Ho = H, Wo = W;
+  if (a.mode == 1) { Ho = (H + 2 - 3) / 2 + 1; Wo = (W + 2 - 3) / 2 + 1; }
+  if (a.mode == 2) { Ho = (H + 1 - 3) / 2 + 1; Wo = (W + 1 - 3) / 2 + 1; }
+  if (a.mode == 3) { Ho = 2 * H; Wo = 2 * W; }
+  const int out_c = a.out_f32 ? 0 : a.out.C;
+  const int Cout = a.cout_valid > 0 ? a.cout_valid : a.out.C;
+  int cin_total = 0;
+  for (auto& s : a.srcs) cin_total += s.C;
+  double flops = 2.0 * N * Ho * Wo * (double)Cout * cin_total * a.ks * a.ks;
+  for (auto& s : a.sc) flops += 2.0 * N * Ho * Wo * (double)Cout * s.C;
+  double bytes = (double)N * Ho * Wo * Cout * (a.out_f32 ? 4 : 2) + (double)a.w->rows * a.w->ktot * a.w->nz * 2;
+  for (auto& s : a.srcs) bytes += (double)s.bytes();
+  for (auto& s : a.sc) bytes += (double)s.bytes();
+  if (a.res1) bytes += (double)a.res1->bytes();
+  if (a.res2) bytes += (double)a.res2->bytes();
+  if (!a.out_f32) GP_REQUIRE(a.out.N == N && a.out.H == Ho && a.out.W == Wo, name + ": output shape mismatch");
+  if (measuring_) return;
+
+  IgemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.flags = a.flags | (bf16_ ? IG_BF16 : 0) | (a.out_f32 ? IG_OUT_F32_NCHW : 0);
+  p.bias = a.w->bias;
+  p.res1 = a.res1 ? ptr(*a.res1) : nullptr;
+  p.res2 = a.res2 ? ptr(*a.res2) : nullptr;
+  p.out = a.out_f32 ? (void*)a.out_f32 : ptr(a.out);
+  p.Cout = Cout;
+  p.BN = choose_bn(Cout, a.force_bn);
+  p.Z1 = 1; p.Z0 = 1;
+  p.out_sy = p.out_sx = 1;
+  const bool tokens = (a.ks == 1 && a.mode == 0 && a.sc.empty() && a.srcs.size() == 1 && !a.out_f32);
+  if (tokens) {
+    const long long ntok = (long long)N * H * W;
+    GP_REQUIRE(ntok < (1LL << 31), name + ": too many tokens");
+    p.gridW = (int)ntok; p.gridH = 1;
+    p.TW = 128; p.TH = 1; p.tw_shift = 7;
+    p.nseg[0] = 1;
+    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(s0.C, 64)};
+    p.outW = (int)ntok; p.outH = 1;
+    p.out_pix_stride = out_c; p.out_row_stride = 0;
+    check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.C, ntok * s0.C, ntok * s0.C, 128, 1, bf16_),
+               name + ": tmap A");
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else {
+    p.Z1 = N;
+    p.a_n_z1 = 1;
+    p.outW = Wo; p.outH = Ho;
+    p.out_pix_stride = out_c;
+    p.out_row_stride = (long long)Wo * out_c;
+    p.out_z1 = (long long)Ho * Wo * out_c;
+    p.gridW = (a.mode == 3) ? W : Wo;
+    p.gridH = (a.mode == 3) ? H : Ho;
+    choose_tile(p.gridW, p.gridH, &p.TW, &p.TH, &p.tw_shift);
+    int nmap = 0;
+    if (a.mode == 0 || a.mode == 3) {
+      GP_REQUIRE(a.srcs.size() + a.sc.size() <= 4, name + ": too many sources");
+      for (auto& s : a.srcs) {
+        GP_REQUIRE(s.N == N && s.H == H && s.W == W, name + ": source shape mismatch");
+        check_cuda(make_tmap_a(&p.tmA[nmap++], ptr(s), s.C, W, H, N, s.C, (long long)W * s.C,
+                               (long long)H * W * s.C, p.TW, p.TH, bf16_), name + ": tmap A");
+      }
+      for (auto& s : a.sc) {
+        GP_REQUIRE(s.N == N && s.H == H && s.W == W && a.mode == 0, name + ": shortcut shape mismatch");
+        check_cuda(make_tmap_a(&p.tmA[nmap++], ptr(s), s.C, W, H, N, s.C, (long long)W * s.C,
+                               (long long)H * W * s.C, p.TW, p.TH, bf16_), name + ": tmap A");
+      }
+    } else {
+      GP_REQUIRE(a.srcs.size() == 1 && a.sc.empty() && H >= 2 && W >= 2, name + ": stride-2 needs one source");
+      for (int hp = 0; hp < 2; ++hp)
+        for (int wp = 0; wp < 2; ++wp) {
+          const uint8_t* b = reinterpret_cast<const uint8_t*>(ptr(s0)) + ((long long)hp * W + wp) * s0.C * 2;
+          check_cuda(make_tmap_a(&p.tmA[hp * 2 + wp], b, s0.C, (W - wp + 1) / 2, (H - hp + 1) / 2, N, 2LL * s0.C,
+                                 2LL * W * s0.C, (long long)H * W * s0.C, p.TW, p.TH, bf16_), name + ": tmap A");
+        }
+      nmap = 4;
+    }
+    for (int i = nmap; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    if (a.mode == 0) {
+      int ns = 0;
+      const int half = a.ks / 2;
+      for (int r = 0; r < a.ks; ++r)
+        for (int s = 0; s < a.ks; ++s)
+          for (size_t i = 0; i < a.srcs.size(); ++i)
+            p.seg[0][ns++] = IgemmSeg{(int8_t)i, (int8_t)(r - half), (int8_t)(s - half), (uint8_t)ceil_div(a.srcs[i].C, 64)};
+      for (size_t j = 0; j < a.sc.size(); ++j)
+        p.seg[0][ns++] = IgemmSeg{(int8_t)(a.srcs.size() + j), 0, 0, (uint8_t)ceil_div(a.sc[j].C, 64)};
+      GP_REQUIRE(ns <= kMaxSegs, name + ": too many K segments");
+      p.nseg[0] = ns;
+    } else if (a.mode == 1 || a.mode == 2) {
+      const int pad = (a.mode == 1) ? 1 : 0;
+      int ns = 0;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          const int ty = r - pad, tx = s - pad;
+          const int hp = ((ty % 2) + 2) % 2, wp = ((tx % 2) + 2) % 2;
+          p.seg[0][ns++] = IgemmSeg{(int8_t)(hp * 2 + wp), (int8_t)((ty - hp) / 2), (int8_t)((tx - wp) / 2),
+                                    (uint8_t)ceil_div(s0.C, 64)};
+        }
+      p.nseg[0] = ns;
+    } else {
+      p.Z0 = 4;
+      p.cls_from_z0 = 1;
+      p.b_z_z0 = 1;
+      p.out_sy = p.out_sx = 2;
+      for (int c = 0; c < 4; ++c) {
+        const int py = c >> 1, px = c & 1;
+        p.cls_py[c] = (int8_t)py; p.cls_px[c] = (int8_t)px;
+        int ns = 0;
+        for (int aa = 0; aa < 2; ++aa)
+          for (int bb = 0; bb < 2; ++bb)
+            p.seg[c][ns++] = IgemmSeg{0, (int8_t)(py - 1 + aa), (int8_t)(px - 1 + bb), (uint8_t)ceil_div(s0.C, 64)};
+        p.nseg[c] = ns;
+      }
+    }
+  }
+  check_cuda(make_tmap_b(&p.tmB, a.w->w, a.w->ktot, a.w->rows, a.w->nz, a.w->ktot, (long long)a.w->rows * a.w->ktot,
+                         p.BN, bf16_), name + ": tmap B");
+  finalize_or_throw(&p, name);
+  const int ncls = p.cls_from_z0 ? p.Z0 : 1;
+  for (int c = 0; c < ncls; ++c)
+    GP_REQUIRE(p.nkb[c] * 64 == a.w->ktot, name + ": packed K (" + std::to_string(a.w->ktot) + ") != planned K (" +
+                                              std::to_string(p.nkb[c] * 64) + ")");
+  GP_REQUIRE(a.w->rows >= Cout || a.w->rows == Cout, name + ": packed rows < Cout");
+  push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
+}
+
+void Builder::attention_qkv(const std::string& name, const void* q, const void* k, long long cs, const void* vT, int B,
+                            int T, int heads, int d, const float* pv_bias, const T4& out) {
+  const int Tp = ceil_div(T, 8) * 8;
+  const int C = heads * d;
+  const size_t s_bytes = (size_t)B * heads * T * Tp * 2;
+  const size_t s_off = arena_.alloc(s_bytes);
+  if (!measuring_) {
+    void* S = raw_ptr(s_off);
+    {  // S = Q K^T  (softmax scale is folded into Wq)
+      IgemmParams p;
+      std::memset(&p, 0, sizeof(p));
+      p.flags = bf16_ ? IG_BF16 : 0;
+      p.gridW = T; p.gridH = 1; p.TW = 128; p.TH = 1; p.tw_shift = 7;
+      p.Z1 = B; p.Z0 = heads;
+      p.a_n_z1 = 1; p.a_k_z0 = d;
+      p.b_z_z1 = 1; p.b_k_z0 = d;
+      p.nseg[0] = 1;
+      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(d, 64)};
+      p.out = S; p.outW = T; p.outH = 1;
+      p.out_pix_stride = Tp; p.out_row_stride = 0;
+      p.out_z1 = (long long)heads * T * Tp; p.out_z0 = (long long)T * Tp;
+      p.out_sy = p.out_sx = 1;
+      p.Cout = T;
+      p.BN = choose_bn(T, 0);
+      check_cuda(make_tmap_a(&p.tmA[0], q, C, T, 1, B, cs, (long long)T * cs, (long long)T * cs, 128, 1, bf16_), name + ": tmap Q");
+      for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+      check_cuda(make_tmap_b(&p.tmB, k, C, T, B, cs, (long long)T * cs, p.BN, bf16_), name + ": tmap K");
+      finalize_or_throw(&p, name + ".qk");
+      push(name + ".qk", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
+           [p](cudaStream_t s) { return igemm_launch(p, s); });
+    }
+    {
+      const long long rows = (long long)B * heads * T;
+      const bool bf = bf16_;
+      push(name + ".softmax", 1, 0, 2.0 * s_bytes, [S, rows, T, Tp, bf](cudaStream_t s) { return softmax_rows(S, rows, T, Tp, bf, s); });
+    }
+    {  // O = P V
+      IgemmParams p;
+      std::memset(&p, 0, sizeof(p));
+      p.flags = bf16_ ? IG_BF16 : 0;
+      p.gridW = T; p.gridH = 1; p.TW = 128; p.TH = 1; p.tw_shift = 7;
+      p.Z1 = B; p.Z0 = heads;
+      p.a_n_z1 = heads; p.a_n_z0 = 1;
+      p.b_z_z1 = 1; p.b_row_z0 = d;
+      p.nseg[0] = 1;
+      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(T, 64)};
+      p.out = ptr(out); p.outW = T; p.outH = 1;
+      p.out_pix_stride = C; p.out_row_stride = 0;
+      p.out_z1 = (long long)T * C; p.out_z0 = d;
+      p.out_sy = p.out_sx = 1;
+      p.Cout = d;
+      p.bias = pv_bias;
+      p.BN = choose_bn(d, 0);
+      check_cuda(make_tmap_a(&p.tmA[0], S, T, T, 1, B * heads, Tp, (long long)T * Tp, (long long)T * Tp, 128, 1, bf16_), name + ": tmap P");
+      for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+      check_cuda(make_tmap_b(&p.tmB, vT, T, C, B, Tp, (long long)C * Tp, p.BN, bf16_), name + ": tmap Vt");
+      finalize_or_throw(&p, name + ".pv");
+      push(name + ".pv", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
+           [p](cudaStream_t s) { return igemm_launch(p, s); });
+    }
+  }
+  arena_.release(s_off);
+}
+
+void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk, const PackedW& wv,
+                        const float* pv_bias, int heads, const T4& out) {
+  const int B = l.N, T = l.H * l.W, C = l.C, d = C / heads;
+  const int Tp = ceil_div(T, 8) * 8;
+  T4 qk = alloc(B, l.H, l.W, 2 * C);
+  {
+    ConvArgs a;
+    a.srcs = {l}; a.ks = 1; a.w = &wqk; a.out = qk;
+    conv(name + ".to_qk", a);
+  }
+  const size_t vt_bytes = (size_t)B * C * Tp * 2;
+  const size_t vt_off = arena_.alloc(vt_bytes);
+  if (!measuring_) {   // V^T[b] = Wv . l[b]^T : A = weights (rows = channels), B = tokens
+    IgemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.flags = bf16_ ? IG_BF16 : 0;
+    p.gridW = C; p.gridH = 1; p.TW = 128; p.TH = 1; p.tw_shift = 7;
+    p.Z1 = B; p.Z0 = 1;
+    p.b_z_z1 = 1;
+    p.nseg[0] = 1;
+    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)(wv.ktot / 64)};
+    p.out = raw_ptr(vt_off); p.outW = C; p.outH = 1;
+    p.out_pix_stride = Tp; p.out_row_stride = 0;
+    p.out_z1 = (long long)C * Tp;
+    p.out_sy = p.out_sx = 1;
+    p.Cout = T;
+    p.BN = choose_bn(T, 0);
+    check_cuda(make_tmap_a(&p.tmA[0], wv.w, wv.ktot, C, 1, 1, wv.ktot, (long long)C * wv.ktot, (long long)C * wv.ktot,
+                           128, 1, bf16_), name + ": tmap Wv");
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    check_cuda(make_tmap_b(&p.tmB, ptr(l), C, T, B, C, (long long)T * C, p.BN, bf16_), name + ": tmap l");
+    finalize_or_throw(&p, name + ".to_vT");
+    push(name + ".to_vT", 1, 2.0 * B * (double)T * C * C, (double)vt_bytes + (double)l.bytes(),
+         [p](cudaStream_t s) { return igemm_launch(p, s); });
+  }
+  const uint16_t* qp = measuring_ ? nullptr : reinterpret_cast<const uint16_t*>(ptr(qk));
+  attention_qkv(name, qp, qp ? qp + C : nullptr, 2 * C, measuring_ ? nullptr : raw_ptr(vt_off), B, T, heads, d, pv_bias, out);
+  arena_.release(vt_off);
+  release(qk);
+}
+
+void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps,
+                 bool silu, const T4& out) {
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  GP_REQUIRE(ctot == out.C && nw.C == ctot && ctot % groups == 0, name + ": GroupNorm channel mismatch");
+  if (measuring_) return;
+  const int N = out.N;
+  const long long HW = (long long)out.H * out.W;
+  float* sums = gn_sums;
+  float* ss = gn_ss;
+  const bool bf = bf16_;
+  std::vector<const void*> xs;
+  std::vector<int> cs;
+  for (auto& s : srcs) { xs.push_back(ptr(s)); cs.push_back(s.C); }
+  void* y = ptr(out);
+  const float* gamma = nw.gamma;
+  const float* beta = nw.beta;
+  double bytes = 0;
+  for (auto& s : srcs) bytes += 2.0 * s.bytes();
+  bytes += (double)out.bytes();
+  push(name, 2 + 2 * (int)srcs.size(), 0, bytes, [=](cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * ctot * 2 * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    int coff = 0;
+    for (size_t i = 0; i < xs.size(); ++i) {
+      e = gn_stats(xs[i], N, HW, cs[i], sums, ctot, coff, bf, s);
+      if (e != cudaSuccess) return e;
+      coff += cs[i];
+    }
+    e = gn_finalize(sums, gamma, beta, N, ctot, groups, HW, eps, ss, s);
+    if (e != cudaSuccess) return e;
+    coff = 0;
+    for (size_t i = 0; i < xs.size(); ++i) {
+      e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s);
+      if (e != cudaSuccess) return e;
+      coff += cs[i];
+    }
+    return cudaSuccess;
+  });
+}
+
+void Builder::ln(const std::string& name, const T4& x, const NormW& nw, float eps, const T4& out) {
+  GP_REQUIRE(nw.C == x.C && out.C == x.C, name + ": LayerNorm channel mismatch");
+  if (measuring_) return;
+  const void* xi = ptr(x);
+  void* yo = ptr(out);
+  const long long tokens = x.pixels();
+  const int C = x.C;
+  const bool bf = bf16_;
+  const float* g = nw.gamma;
+  const float* b = nw.beta;
+  push(name, 1, 0, 2.0 * x.bytes(), [=](cudaStream_t s) { return layernorm(xi, yo, tokens, C, g, b, eps, bf, s); });
+}
+
+void Builder::xattn(const std::string& name, const T4& x, const XattnW& w, float eps, const T4& out) {
+  GP_REQUIRE(w.C == x.C, name + ": cross-attention channel mismatch");
+  if (measuring_) return;
+  const void* xi = ptr(x);
+  void* yo = ptr(out);
+  const long long tokens = x.pixels();
+  const bool bf = bf16_;
+  const XattnW ww = w;
+  push(name, 1, 4.0 * tokens * (double)w.C * w.heads, 2.0 * x.bytes(), [=](cudaStream_t s) {
+    return xattn2(xi, yo, tokens, ww.C, ww.heads, ww.U, ww.u0, ww.M, ww.c0, eps, bf, s);
+  });
+}
+
+void Builder::geglu_op(const std::string& name, const T4& in, const T4& out) {
+  if (measuring_) return;
+  const void* xi = ptr(in);
+  void* yo = ptr(out);
+  const long long tokens = in.pixels();
+  const int c4 = out.C;
+  const bool bf = bf16_;
+  push(name, 1, 0, (double)in.bytes() + out.bytes(), [=](cudaStream_t s) { return geglu(xi, yo, tokens, c4, bf, s); });
+}
+
+void Builder::relu_op(const std::string& name, const T4& in, const T4& out) {
+  if (measuring_) return;
+  const void* xi = ptr(in);
+  void* yo = ptr(out);
+  const long long n = in.pixels() * in.C;
+  const bool bf = bf16_;
+  push(name, 1, 0, 2.0 * in.bytes(), [=](cudaStream_t s) { return relu16(xi, yo, n, bf, s); });
+}
+
+void Builder::bilinear(const std::string& name, const T4& in, const T4& out) {
+  GP_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C, name + ": bilinear shape mismatch");
+  if (measuring_) return;
+  const void* xi = ptr(in);
+  void* yo = ptr(out);
+  const T4 t = in;
+  const bool bf = bf16_;
+  push(name, 1, 0, (double)in.bytes() + out.bytes(), [=](cudaStream_t s) { return bilinear_up2x(xi, yo, t.N, t.H, t.W, t.C, bf, s); });
+}
+
+void Builder::direct(const std::string& name, const T4& in, int cin, const DirectW& w, const T4& out, int flags,
+                     float* out_f32, int up) {
+  GP_REQUIRE(w.Cin == cin, name + ": direct conv channel mismatch");
+  if (measuring_) return;
+  DirectConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.in = ptr(in);
+  p.N = in.N; p.H = in.H; p.W = in.W; p.Cin = cin; p.in_cstride = in.C;
+  p.w = w.w; p.bias = w.bias;
+  p.Ho = up ? 2 * in.H : in.H; p.Wo = up ? 2 * in.W : in.W;
+  p.Cout = w.Cout;
+  p.ks = w.ks; p.stride = 1; p.pad = w.ks / 2;
+  p.flags = flags | (up ? DC_UP2X : 0) | (out_f32 ? DC_OUT_F32_NCHW : 0);
+  if (out_f32) { p.out = out_f32; p.out_cstride = w.Cout; }
+  else { p.out = ptr(out); p.out_cstride = out.C; }
+  const bool bf = bf16_;
+  const double flops = 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * cin * w.ks * w.ks;
+  push(name, 1, flops, (double)in.bytes() + (double)p.N * p.Ho * p.Wo * p.Cout * (out_f32 ? 4 : 2),
+       [p, bf](cudaStream_t s) { return direct_conv(p, bf, s); });
+}
+
+}  // namespace gp

@@ -1,0 +1,402 @@
+// tcgen05 implicit-GEMM kernel (see igemm.h for the operand model).
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over a static round-robin tile list):
+//   warp 0 lane 0 : TMA producer  (A box + B box per 64-channel K block, `stages`-deep ring)
+//   warp 1 lane 0 : MMA issuer    (4 x tcgen05.mma 128xBNx16 per K block; commit frees the slot)
+//   warp 2        : TMEM allocator (512 columns = 2 accumulator buffers of up to 256 columns)
+//   warps 4..7    : epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/residual/act -> HBM)
+#include "igemm.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "ptx.cuh"
+
+namespace gp {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kABytes = kBM * kBK * 2;       // 16 KiB
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;              // TMEM columns between the two accumulator buffers
+constexpr int kMaxSmem = 227 * 1024;
+
+struct TileCoord {
+  int n_tile, tx, ty, z0, z1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles_n;
+  int r = tile / p.n_tiles_n;
+  t.tx = r % p.tiles_x;
+  r /= p.tiles_x;
+  t.ty = r % p.tiles_y;
+  r /= p.tiles_y;
+  t.z0 = r % p.Z0;
+  t.z1 = r / p.Z0;
+  return t;
+}
+
+template <bool BF16>
+__device__ __forceinline__ float cvt16(uint16_t v) {
+  if constexpr (BF16) {
+    return __bfloat162float(__ushort_as_bfloat16(v));
+  } else {
+    return __half2float(__ushort_as_half(v));
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABytes + p.BN * 128;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int cls = p.cls_from_z0 ? t.z0 : 0;
+      const int a_n = t.z1 * p.a_n_z1 + t.z0 * p.a_n_z0;
+      const int a_k0 = t.z0 * p.a_k_z0;
+      const int b_z = t.z1 * p.b_z_z1 + t.z0 * p.b_z_z0;
+      const int b_row = t.z0 * p.b_row_z0 + t.n_tile * p.BN;
+      const int b_k0 = t.z0 * p.b_k_z0;
+      const int x0 = t.tx * p.TW, y0 = t.ty * p.TH;
+      int kb = 0;
+      const int ns = p.nseg[cls];
+      for (int s = 0; s < ns; ++s) {
+        const IgemmSeg sg = p.seg[cls][s];
+        for (int c = 0; c < sg.nchunks; ++c, ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          uint8_t* sA = smem + stage * stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_4d(sA, &p.tmA[sg.map], &full_bar[stage], a_k0 + c * kBK, x0 + sg.dx, y0 + sg.dy, a_n);
+          tma_load_3d(sB, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int cls = p.cls_from_z0 ? t.z0 : 0;
+      const int nkb = p.nkb[cls];
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+        const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
+          umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int wq = warp - 4;                 // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
+    const int row = wq * 32 + lane;
+    const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool f32out = (p.flags & IG_OUT_F32_NCHW) != 0;
+    const bool relu = (p.flags & IG_RELU) != 0;
+    const bool aff = (p.flags & IG_AFFINE_CLAMP01) != 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int cls = p.cls_from_z0 ? t.z0 : 0;
+      const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
+      const bool valid = gy < p.gridH && gx < p.gridW;
+      const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
+      const long long pix_off = t.z1 * p.out_z1 + t.z0 * p.out_z0 + (long long)oy * p.out_row_stride +
+                                (long long)ox * p.out_pix_stride;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride;
+      const int n_base = t.n_tile * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        const int ncols = (p.BN - c0 >= 32) ? 32 : 16;
+        if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
+        tmem_ld_wait();
+        const int n0 = n_base + c0;
+        if (!valid || n0 >= p.Cout) continue;
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+        const int nvalid = min(ncols, p.Cout - n0);
+        if (p.bias != nullptr) {
+          if (nvalid == 32) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q));
+              v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += __ldg(p.bias + n0 + q);
+          }
+        }
+        if (f32out) {
+          float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            if (q < nvalid) {
+              float x = v[q];
+              if (relu) x = fmaxf(x, 0.f);
+              if (aff) x = fminf(fmaxf((x + 1.f) * 0.5f, 0.f), 1.f);
+              o[(((long long)t.z1 * p.Cout + (n0 + q)) * p.outH + oy) * p.outW + ox] = x;
+            }
+          }
+          continue;
+        }
+        const long long off = pix_off + n0;
+        const bool vec = (nvalid == ncols) && ((off & 7) == 0);
+        if (p.res1 != nullptr) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res1) + off;
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (q < ncols) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[q + 2 * e] += cvt16<BF16>((uint16_t)(w[e] & 0xFFFF));
+                  v[q + 2 * e + 1] += cvt16<BF16>((uint16_t)(w[e] >> 16));
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
+          }
+        }
+        if (p.res2 != nullptr) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res2) + off;
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (q < ncols) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[q + 2 * e] += cvt16<BF16>((uint16_t)(w[e] & 0xFFFF));
+                  v[q + 2 * e + 1] += cvt16<BF16>((uint16_t)(w[e] >> 16));
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            if (q < ncols) {
+              uint4 u;
+              u.x = pack16<BF16>(v[q], v[q + 1]);
+              u.y = pack16<BF16>(v[q + 2], v[q + 3]);
+              u.z = pack16<BF16>(v[q + 4], v[q + 5]);
+              u.w = pack16<BF16>(v[q + 6], v[q + 7]);
+              *reinterpret_cast<uint4*>(op + q) = u;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(f);
+  return fn;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+cudaError_t make_tmap_a(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW,
+                        long long sH, long long sN, int TW, int TH, bool bf16) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t make_tmap_b(CUtensorMap* m, const void* base, long long K, long long rows, long long Z,
+                        long long sRow, long long sZ, int BN, bool bf16) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)Z};
+  cuuint64_t strides[2] = {(cuuint64_t)sRow * 2, (cuuint64_t)sZ * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+size_t igemm_smem_bytes(const IgemmParams& p) {
+  return (size_t)p.stages * (kABytes + p.BN * 128) + (2 * p.stages + 4) * 8 + 16 + 1024;
+}
+
+const char* igemm_finalize(IgemmParams* p) {
+  if (p->TW * p->TH != kBM) return "TW*TH must be 128";
+  if ((1 << p->tw_shift) != p->TW) return "TW must be a power of two";
+  if (p->BN < 16 || p->BN > 256 || (p->BN % 16)) return "BN must be a multiple of 16 in [16,256]";
+  if (p->Z0 < 1 || p->Z1 < 1) return "bad batch dims";
+  p->tiles_x = (p->gridW + p->TW - 1) / p->TW;
+  p->tiles_y = (p->gridH + p->TH - 1) / p->TH;
+  p->n_tiles_n = (p->Cout + p->BN - 1) / p->BN;
+  const int ncls = p->cls_from_z0 ? p->Z0 : 1;
+  if (ncls > kMaxClasses) return "too many classes";
+  for (int c = 0; c < ncls; ++c) {
+    if (p->nseg[c] < 1 || p->nseg[c] > kMaxSegs) return "bad segment count";
+    int n = 0;
+    for (int s = 0; s < p->nseg[c]; ++s) n += p->seg[c][s].nchunks;
+    p->nkb[c] = n;
+    if (n < 1) return "empty K loop";
+  }
+  long long total = (long long)p->n_tiles_n * p->tiles_x * p->tiles_y * p->Z0 * p->Z1;
+  if (total > 0x7fffffffLL) return "too many tiles";
+  p->total_tiles = (int)total;
+  const int stage_bytes = kABytes + p->BN * 128;
+  int st = (kMaxSmem - 2048) / stage_bytes;
+  if (st > 8) st = 8;
+  if (st < 2) return "tile too large for shared memory";
+  p->stages = st;
+  return nullptr;
+}
+
+cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  if (p.total_tiles <= 0) return cudaSuccess;
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  // always request the maximum so exactly one CTA (512 TMEM columns) is resident per SM
+  const size_t smem = kMaxSmem;
+  if (p.flags & IG_BF16)
+    igemm_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+  else
+    igemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace gp

@@ -1,0 +1,79 @@
+// Persistent warp-specialised tcgen05 implicit-GEMM: the one tensor-core kernel behind every 3x3
+// convolution (stride 1, stride 2, nearest-2x-upsample-fused), 1x1 convolution / linear layer
+// and batched attention GEMM of the hot path.
+//
+//   D[pixel, n] = sum over K-segments s, channels c :  A_s[pixel + (dy_s, dx_s), c] * B[n, k(s, c)]
+//
+// A operand: up to 4 NHWC activation views, each a 4-D TMA tensor map (C, W, H, N); a CTA's
+// 128-row M tile is a TW x TH spatial patch, loaded per K-chunk of 64 channels as one TMA box whose
+// start coordinate carries the filter-tap offset (halo/padding = TMA out-of-bounds zero fill).
+// B operand: K-major [rows, K] matrix (packed weights, or activations for attention), 3-D map.
+// Accumulators: fp32 in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gp {
+
+constexpr int kMaxSegs = 20;
+constexpr int kMaxClasses = 4;
+constexpr int kBM = 128;      // UMMA M (TMEM lanes)
+constexpr int kBK = 64;       // channels per pipeline stage (= one 128-byte swizzle row of fp16)
+
+struct IgemmSeg {
+  int8_t map;        // index into tmA
+  int8_t dy, dx;     // tap offset in the map's pixel grid
+  uint8_t nchunks;   // ceil(C / 64)
+};
+
+enum IgemmFlags : int {
+  IG_RELU = 1,            // max(v, 0) after bias/residual
+  IG_OUT_F32_NCHW = 2,    // write fp32 planar [Z1, Cout, outH, outW] instead of 16-bit NHWC
+  IG_AFFINE_CLAMP01 = 4,  // v = clamp((v + 1) / 2, 0, 1)   (genpercept_pipeline.py:470-472)
+  IG_BF16 = 8,            // operands / 16-bit outputs are bf16 instead of fp16
+};
+
+struct IgemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  IgemmSeg seg[kMaxClasses][kMaxSegs];
+  int nseg[kMaxClasses];
+  int nkb[kMaxClasses];          // total K blocks per class
+  int8_t cls_py[kMaxClasses], cls_px[kMaxClasses];
+  int out_sy, out_sx;            // output pixel = tile-grid pixel * s + (py, px)
+  int TW, TH, tw_shift;          // M tile = TH rows x TW cols, TW*TH == 128, TW = 1 << tw_shift
+  int tiles_x, tiles_y, n_tiles_n, BN;
+  int gridW, gridH;              // valid extent of the tile grid (pixels)
+  int Z1, Z0;                    // batch dims (z1 outer: image; z0 inner: parity class / head)
+  int cls_from_z0;
+  int a_n_z1, a_n_z0, a_k_z0;                    // A coords: n = z1*a_n_z1 + z0*a_n_z0 ; k0 = z0*a_k_z0
+  int b_z_z1, b_z_z0, b_row_z0, b_k_z0;          // B coords
+  long long out_z1, out_z0;                      // output element offsets per batch index
+  void* out;
+  int outW, outH;
+  long long out_pix_stride;      // elements between consecutive pixels of a row (16-bit NHWC mode)
+  long long out_row_stride;      // elements between rows
+  int Cout;                      // valid output columns
+  const float* bias;             // [Cout] or null
+  const void* res1;              // same addressing as out, or null
+  const void* res2;
+  int flags;
+  int stages;
+  int total_tiles;
+};
+
+// host helpers ----------------------------------------------------------------------------------
+// Encode a 4-D NHWC view (C, W, H, N) with element strides (sW, sH, sN) and box (64, TW, TH, 1).
+cudaError_t make_tmap_a(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW,
+                        long long sH, long long sN, int TW, int TH, bool bf16);
+// Encode a 3-D K-major matrix view (K, rows, Z) with element strides (sRow, sZ) and box (64, BN, 1).
+cudaError_t make_tmap_b(CUtensorMap* m, const void* base, long long K, long long rows, long long Z,
+                        long long sRow, long long sZ, int BN, bool bf16);
+// Fill tile counts / stage count and validate; returns nullptr or an error string.
+const char* igemm_finalize(IgemmParams* p);
+cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream);
+size_t igemm_smem_bytes(const IgemmParams& p);
+
+}  // namespace gp

@@ -1,0 +1,595 @@
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace gp {
+namespace {
+
+template <bool BF16>
+__device__ __forceinline__ float f16_to_f32(uint16_t v) {
+  if constexpr (BF16) return __bfloat162float(__ushort_as_bfloat16(v));
+  else return __half2float(__ushort_as_half(v));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t f32_to_f16(float v) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  else return __half_as_ushort(__float2half_rn(v));
+}
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = f16_to_f32<BF16>((uint16_t)(w[e] & 0xFFFF));
+    f[2 * e + 1] = f16_to_f32<BF16>((uint16_t)(w[e] >> 16));
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    w[e] = (uint32_t)f32_to_f16<BF16>(f[2 * e]) | ((uint32_t)f32_to_f16<BF16>(f[2 * e + 1]) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------ direct conv
+template <bool BF16>
+__global__ void direct_conv_kernel(const DirectConvParams p) {
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % p.Cout);
+  long long r = idx / p.Cout;
+  const int ox = (int)(r % p.Wo);
+  r /= p.Wo;
+  const int oy = (int)(r % p.Ho);
+  const int n = (int)(r / p.Ho);
+  const bool up = (p.flags & DC_UP2X) != 0;
+  const int He = up ? 2 * p.H : p.H, We = up ? 2 * p.W : p.W;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
+  float acc = p.bias ? p.bias[co] : 0.f;
+  for (int ky = 0; ky < p.ks; ++ky) {
+    int iy = oy * p.stride + ky - p.pad;
+    if (iy < 0 || iy >= He) continue;
+    if (up) iy >>= 1;
+    for (int kx = 0; kx < p.ks; ++kx) {
+      int ix = ox * p.stride + kx - p.pad;
+      if (ix < 0 || ix >= We) continue;
+      if (up) ix >>= 1;
+      const uint16_t* xp = in + (((long long)n * p.H + iy) * p.W + ix) * p.in_cstride;
+      const float* wp = p.w + ((long long)(ky * p.ks + kx) * p.Cin) * p.Cout + co;
+      for (int ci = 0; ci < p.Cin; ++ci) acc += f16_to_f32<BF16>(xp[ci]) * wp[(long long)ci * p.Cout];
+    }
+  }
+  const long long opix = ((long long)n * p.Ho + oy) * p.Wo + ox;
+  if (p.res) acc += f16_to_f32<BF16>(reinterpret_cast<const uint16_t*>(p.res)[opix * p.out_cstride + co]);
+  if (p.flags & DC_RELU) acc = fmaxf(acc, 0.f);
+  if (p.flags & DC_AFFINE_CLAMP01) acc = fminf(fmaxf((acc + 1.f) * 0.5f, 0.f), 1.f);
+  if (p.flags & DC_OUT_F32_NCHW) {
+    reinterpret_cast<float*>(p.out)[(((long long)n * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = acc;
+  } else {
+    reinterpret_cast<uint16_t*>(p.out)[opix * p.out_cstride + co] = f32_to_f16<BF16>(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------ GroupNorm
+template <bool BF16>
+__global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, int C, float* sums, int Ctot,
+                                int coff, int pix_per_block) {
+  extern __shared__ float sh[];   // [C][2]
+  const int n = blockIdx.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2 * C; i += nthr) sh[i] = 0.f;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > HW) p1 = HW;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  const uint16_t* base = x + ((long long)n * HW) * C + threadIdx.x * 8;
+  for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * C));
+    float f[8];
+    unpack8<BF16>(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(&sh[(threadIdx.x * 8 + e) * 2], s[e]);
+    atomicAdd(&sh[(threadIdx.x * 8 + e) * 2 + 1], q[e]);
+  }
+  __syncthreads();
+  float* dst = sums + ((long long)n * Ctot + coff) * 2;
+  for (int i = tid; i < 2 * C; i += nthr) atomicAdd(&dst[i], sh[i]);
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int N, int Ctot, int groups, float inv_count,
+                                   float eps, float* __restrict__ ss) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * Ctot) return;
+  const int n = idx / Ctot, c = idx % Ctot;
+  const int cpg = Ctot / groups;
+  const int g0 = (c / cpg) * cpg;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < cpg; ++i) {
+    s += sums[((long long)n * Ctot + g0 + i) * 2];
+    q += sums[((long long)n * Ctot + g0 + i) * 2 + 1];
+  }
+  const float mean = s * inv_count;
+  const float var = fmaxf(q * inv_count - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float sc = rstd * gamma[c];
+  ss[(long long)idx * 2] = sc;
+  ss[(long long)idx * 2 + 1] = beta[c] - mean * sc;
+}
+
+template <bool BF16, bool SILU>
+__global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, int C, const float* __restrict__ ss,
+                                int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, long long total_vec) {
+  const int nvec = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const long long pix = i / nvec;           // n*HW + p
+    const int n = (int)(pix / HW);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * C + v * 8));
+    float f[8];
+    unpack8<BF16>(u, f);
+    const float4* sp = reinterpret_cast<const float4*>(ss + ((long long)n * Ctot + coff + v * 8) * 2);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 a = __ldg(sp + e);       // (scale, shift) x 2 channels
+      float y0 = f[2 * e] * a.x + a.y, y1 = f[2 * e + 1] * a.z + a.w;
+      if (SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      f[2 * e] = y0; f[2 * e + 1] = y1;
+    }
+    *reinterpret_cast<uint4*>(y + pix * y_cstride + coff + v * 8) = pack8<BF16>(f);
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+constexpr int kLnMaxVec = 5;   // C <= 1280
+template <bool BF16>
+__global__ void layernorm_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int nvec = C / 8;
+  float f[kLnMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + tok * C + v * 8)), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * __ldg(gamma + v * 8 + e) + __ldg(beta + v * 8 + e);
+      *reinterpret_cast<uint4*>(y + tok * C + v * 8) = pack8<BF16>(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ row softmax
+constexpr int kSmMaxVec = 8;   // T <= 256 threads * 8 vec * 8 = 16384
+template <bool BF16>
+__global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long rows, int T, int Tp) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  uint16_t* row = s + r * Tp;
+  float m = -INFINITY;
+  for (int i = lane; i < T; i += 32) m = fmaxf(m, f16_to_f32<BF16>(row[i]));
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int i = lane; i < T; i += 32) sum += __expf(f16_to_f32<BF16>(row[i]) - m);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = lane; i < T; i += 32) row[i] = f32_to_f16<BF16>(__expf(f16_to_f32<BF16>(row[i]) - m) * inv);
+}
+
+template <bool BF16>
+__global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
+  __shared__ float red[32];
+  uint16_t* row = s + (long long)blockIdx.x * Tp;
+  const int nvec = T / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float f[kSmMaxVec][8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(row + v * 8), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, f[i][e]);
+    }
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < nwarp; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    if (threadIdx.x + i * blockDim.x < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { f[i][e] = __expf(f[i][e] - m); sum += f[i][e]; }
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < nwarp; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[i][e] *= inv;
+      *reinterpret_cast<uint4*>(row + v * 8) = pack8<BF16>(f[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ 2-token cross attention
+template <bool BF16>
+__global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens, int C,
+                              int heads, const float* __restrict__ U, const float* __restrict__ u0,
+                              const float* __restrict__ M, const float* __restrict__ c0, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int nvec = C / 8;
+  float f[kLnMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + tok * C + v * 8)), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  float acc[kLnMaxVec][8];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[i][e] = f[i][e] + __ldg(c0 + v * 8 + e);
+    }
+  }
+  for (int h = 0; h < heads; ++h) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(U + (long long)h * C + v * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(U + (long long)h * C + v * 8 + 4));
+        d += (f[i][0] - mean) * a.x + (f[i][1] - mean) * a.y + (f[i][2] - mean) * a.z + (f[i][3] - mean) * a.w +
+             (f[i][4] - mean) * b.x + (f[i][5] - mean) * b.y + (f[i][6] - mean) * b.z + (f[i][7] - mean) * b.w;
+      }
+    }
+    d = warp_sum(d) * rstd + __ldg(u0 + h);
+    const float pr = 1.f / (1.f + __expf(-d));
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(M + (long long)h * C + v * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(M + (long long)h * C + v * 8 + 4));
+        acc[i][0] += pr * a.x; acc[i][1] += pr * a.y; acc[i][2] += pr * a.z; acc[i][3] += pr * a.w;
+        acc[i][4] += pr * b.x; acc[i][5] += pr * b.y; acc[i][6] += pr * b.z; acc[i][7] += pr * b.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) *reinterpret_cast<uint4*>(y + tok * C + v * 8) = pack8<BF16>(acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------ elementwise
+template <bool BF16>
+__global__ void geglu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec, int C4) {
+  const int nvec = C4 / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i / nvec;
+    const int v = (int)(i % nvec);
+    float a[8], g[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(in + tok * 2 * C4 + v * 8)), a);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(in + tok * 2 * C4 + C4 + v * 8)), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] *= 0.5f * g[e] * (1.f + erff(g[e] * 0.70710678118654752f));
+    *reinterpret_cast<uint4*>(out + tok * C4 + v * 8) = pack8<BF16>(a);
+  }
+}
+
+template <bool BF16>
+__global__ void relu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(in + i * 8)), a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8<BF16>(a);
+  }
+}
+
+template <bool BF16>
+__global__ void bilinear_up2x_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W,
+                                     int C, float sy, float sx, long long total_vec) {
+  const int nvec = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long r = i / nvec;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float h1 = fy - y0, w1 = fx - x0, h0 = 1.f - h1, w0 = 1.f - w1;
+    const uint16_t* b = in + ((long long)n * H * W) * C + v * 8;
+    float a00[8], a01[8], a10[8], a11[8], o[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x0) * C)), a00);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x1) * C)), a01);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x0) * C)), a10);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x1) * C)), a11);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = h0 * (w0 * a00[e] + w1 * a01[e]) + h1 * (w0 * a10[e] + w1 * a11[e]);
+    *reinterpret_cast<uint4*>(out + (((long long)n * Ho + oy) * Wo + ox) * C + v * 8) = pack8<BF16>(o);
+  }
+}
+
+template <bool BF16>
+__global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_t* __restrict__ out, int N,
+                                  long long HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  const int n = (int)(i / HW);
+  const long long p = i % HW;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long off = ((long long)n * 3 + c) * HW + p;
+    if (kind == 0) f[c] = (float)reinterpret_cast<const uint8_t*>(in)[off] / 255.0f * 2.0f - 1.0f;
+    else if (kind == 1) f[c] = f16_to_f32<false>(reinterpret_cast<const uint16_t*>(in)[off]);
+    else f[c] = reinterpret_cast<const float*>(in)[off];
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = pack8<BF16>(f);
+}
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__global__ void minmax_init_kernel(unsigned int* s, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) { s[2 * i] = 0xFFFFFFFFu; s[2 * i + 1] = 0u; }
+}
+__global__ void minmax_reduce_kernel(const float* __restrict__ x, long long HW, unsigned int* s) {
+  const int n = blockIdx.y;
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[(long long)n * HW + i];
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  mn = -warp_max(-mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s[2 * n], f2ord(mn)); atomicMax(&s[2 * n + 1], f2ord(mx)); }
+}
+__global__ void minmax_apply_kernel(float* __restrict__ x, long long HW, const unsigned int* __restrict__ s) {
+  const int n = blockIdx.y;
+  const float mn = ord2f(s[2 * n]), mx = ord2f(s[2 * n + 1]);
+  const float d = mx - mn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+    x[(long long)n * HW + i] = (x[(long long)n * HW + i] - mn) / d;
+}
+
+inline int blocks_for(long long total, int threads, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+#define GP_DISPATCH_BF16(bf16, ...) \
+  do {                              \
+    if (bf16) {                     \
+      constexpr bool BF = true;     \
+      __VA_ARGS__;                  \
+    } else {                        \
+      constexpr bool BF = false;    \
+      __VA_ARGS__;                  \
+    }                               \
+  } while (0)
+
+cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s) {
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  if (total <= 0) return cudaSuccess;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  GP_DISPATCH_BF16(bf16, (direct_conv_kernel<BF><<<(unsigned)blocks, threads, 0, s>>>(p)));
+  return cudaGetLastError();
+}
+
+cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* sums, int Ctot, int coff, bool bf16,
+                     cudaStream_t s) {
+  const int nvec = C / 8;
+  int pix = 256 / nvec;
+  if (pix < 1) pix = 1;
+  if (pix > 32) pix = 32;
+  const int pix_per_block = pix * 64;
+  dim3 block(nvec, pix);
+  dim3 grid((unsigned)((HW + pix_per_block - 1) / pix_per_block), N);
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  GP_DISPATCH_BF16(bf16, (gn_stats_kernel<BF><<<grid, block, smem, s>>>(reinterpret_cast<const uint16_t*>(x), HW, C,
+                                                                         sums, Ctot, coff, pix_per_block)));
+  return cudaGetLastError();
+}
+
+cudaError_t gn_finalize(const float* sums, const float* gamma, const float* beta, int N, int Ctot, int groups,
+                        long long HW, float eps, float* ss, cudaStream_t s) {
+  const int total = N * Ctot;
+  const float inv_count = 1.0f / ((float)HW * (float)(Ctot / groups));
+  gn_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(sums, gamma, beta, N, Ctot, groups, inv_count, eps, ss);
+  return cudaGetLastError();
+}
+
+cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* ss, int Ctot, int coff, void* y,
+                     int y_cstride, bool silu, bool bf16, cudaStream_t s) {
+  const long long total_vec = (long long)N * HW * (C / 8);
+  const int blocks = blocks_for(total_vec, 256);
+  const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
+  uint16_t* yo = reinterpret_cast<uint16_t*>(y);
+  if (silu)
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<blocks, 256, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, total_vec)));
+  else
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<blocks, 256, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, total_vec)));
+  return cudaGetLastError();
+}
+
+cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const float* gamma, const float* beta,
+                      float eps, bool bf16, cudaStream_t s) {
+  if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
+  const int tpb = 8;
+  const long long blocks = (tokens + tpb - 1) / tpb;
+  GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF><<<(unsigned)blocks, tpb * 32, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), tokens, C, gamma,
+                             beta, eps)));
+  return cudaGetLastError();
+}
+
+cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cudaStream_t s) {
+  if (T % 8 || Tp % 8 || T < 64) {
+    const int wpb = 8;
+    GP_DISPATCH_BF16(bf16, (softmax_rows_small_kernel<BF><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+                               reinterpret_cast<uint16_t*>(sio), rows, T, Tp)));
+    return cudaGetLastError();
+  }
+  if (T / 8 > 256 * kSmMaxVec) return cudaErrorInvalidValue;
+  int threads = ((T / 8 + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 32) threads = 32;
+  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
+  return cudaGetLastError();
+}
+
+cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, const float* U, const float* u0,
+                   const float* M, const float* c0, float eps, bool bf16, cudaStream_t s) {
+  if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
+  const int tpb = 8;
+  const long long blocks = (tokens + tpb - 1) / tpb;
+  GP_DISPATCH_BF16(bf16, (xattn2_kernel<BF><<<(unsigned)blocks, tpb * 32, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), tokens, C, heads, U,
+                             u0, M, c0, eps)));
+  return cudaGetLastError();
+}
+
+cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16, cudaStream_t s) {
+  const long long total_vec = tokens * (C4 / 8);
+  GP_DISPATCH_BF16(bf16, (geglu_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec, C4)));
+  return cudaGetLastError();
+}
+
+cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s) {
+  const long long total_vec = n / 8;
+  GP_DISPATCH_BF16(bf16, (relu_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec)));
+  return cudaGetLastError();
+}
+
+cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16, cudaStream_t s) {
+  const long long total_vec = (long long)N * 4 * H * W * (C / 8);
+  const float sy = H > 1 ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
+  const float sx = W > 1 ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
+  GP_DISPATCH_BF16(bf16, (bilinear_up2x_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, C, sy,
+                             sx, total_vec)));
+  return cudaGetLastError();
+}
+
+cudaError_t preprocess_rgb(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s) {
+  const long long HW = (long long)H * W;
+  const long long total = (long long)N * HW;
+  GP_DISPATCH_BF16(bf16, (preprocess_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                             in, in_kind, reinterpret_cast<uint16_t*>(out), N, HW)));
+  return cudaGetLastError();
+}
+
+cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s) {
+  minmax_init_kernel<<<(N + 63) / 64, 64, 0, s>>>(scratch, N);
+  int bx = (int)((HW + 256 * 8 - 1) / (256 * 8));
+  if (bx > 256) bx = 256;
+  if (bx < 1) bx = 1;
+  minmax_reduce_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch);
+  minmax_apply_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch);
+  return cudaGetLastError();
+}
+
+}  // namespace gp

@@ -1,0 +1,58 @@
+// Bandwidth-bound and small kernels of the hot path (everything that is not a dense contraction):
+// GroupNorm(+SiLU), LayerNorm, row softmax, the 2-token cross-attention closed form, GEGLU,
+// ReLU, bilinear 2x, direct convolution for tiny channel counts (and as the on-device triage
+// reference for the tcgen05 kernel), pre/post-processing.  16-bit NHWC activations, fp32 math.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gp {
+
+enum DirectConvFlags : int {
+  DC_RELU = 1,
+  DC_OUT_F32_NCHW = 2,
+  DC_AFFINE_CLAMP01 = 4,
+  DC_UP2X = 8,          // input is nearest-2x upsampled before the convolution
+};
+
+struct DirectConvParams {
+  const void* in;       // 16-bit NHWC, channel stride in_cstride
+  int N, H, W, Cin, in_cstride;
+  const float* w;       // fp32 [ks*ks][Cin][Cout]
+  const float* bias;    // fp32 [Cout] or null
+  const void* res;      // 16-bit NHWC (out_cstride) or null
+  void* out;
+  int Ho, Wo, Cout, out_cstride;
+  int ks, stride, pad;  // pad = leading zero padding (trailing padding is implicit)
+  int flags;
+};
+cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s);
+
+// GroupNorm: per-(n, channel) sum / sum-of-squares -> per-(n, channel) scale / shift -> apply.
+cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* sums /*[N][Ctot][2]*/, int Ctot,
+                     int coff, bool bf16, cudaStream_t s);
+cudaError_t gn_finalize(const float* sums, const float* gamma, const float* beta, int N, int Ctot,
+                        int groups, long long HW, float eps, float* scale_shift /*[N][Ctot][2]*/,
+                        cudaStream_t s);
+cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* scale_shift, int Ctot,
+                     int coff, void* y, int y_cstride, bool silu, bool bf16, cudaStream_t s);
+
+cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const float* gamma,
+                      const float* beta, float eps, bool bf16, cudaStream_t s);
+// in-place softmax over the first T entries of each row (row stride Tp elements)
+cudaError_t softmax_rows(void* s_inout, long long rows, int T, int Tp, bool bf16, cudaStream_t s);
+// y = x + c0 + sigmoid(LN(x) . U + u0) . M     (U already carries LN gamma, u0 beta)
+cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, const float* U /*[h][C]*/,
+                   const float* u0 /*[h]*/, const float* M /*[h][C]*/, const float* c0 /*[C]*/,
+                   float eps, bool bf16, cudaStream_t s);
+cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16, cudaStream_t s);
+cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s);
+cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16,
+                          cudaStream_t s);
+// u8 / f16 / f32 NCHW [N,3,H,W] -> 16-bit NHWC8 (channels 3..7 zero); u8 is mapped x/255*2-1.
+cudaError_t preprocess_rgb(const void* in, int in_kind /*0 u8, 1 f16, 2 f32*/, void* out, int N, int H,
+                           int W, bool bf16, cudaStream_t s);
+// per-image (x - min) / (max - min) over HW fp32 values, in place; scratch: 2 uint32 per image.
+cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s);
+
+}  // namespace gp

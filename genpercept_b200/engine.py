@@ -1,0 +1,270 @@
+"""ctypes binding of libgenpercept_b200.so (include/genpercept_b200.h).
+
+PyTorch is used only for device memory, streams and dtype bookkeeping; every numerical op of the
+hot path runs inside the native library.  There is no CPU fallback: if the library or a CUDA device
+is missing, construction raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgenpercept_b200.so")
+
+GP_F32, GP_F16, GP_BF16, GP_U8 = 0, 1, 2, 3
+GP_READOUT_VAE, GP_READOUT_DPT = 0, 1
+STAGE_PRE, STAGE_VAE_ENCODE, STAGE_UNET, STAGE_READOUT = 0, 1, 2, 3
+_STATUS = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_MISSING", 3: "GP_ERR_NO_PLAN", 4: "GP_ERR_CUDA",
+           5: "GP_ERR_STATE"}
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("device", c_int), ("dtype", c_int), ("readout", c_int), ("timestep", c_int),
+                ("use_cuda_graph", c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the native library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -m genpercept_b200.build` "
+                           "(or __graft_entry__.build()); there is no fallback path")
+    L = ctypes.CDLL(LIB_PATH)
+    L.gp_create.argtypes = [POINTER(_Config), POINTER(c_void_p)]
+    L.gp_destroy.argtypes = [c_void_p]
+    L.gp_destroy.restype = None
+    L.gp_last_error.argtypes = [c_void_p]
+    L.gp_last_error.restype = c_char_p
+    L.gp_load_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64), c_int]
+    L.gp_set_text_embed.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    L.gp_finalize.argtypes = [c_void_p]
+    L.gp_plan.argtypes = [c_void_p, c_int, c_int, c_int]
+    L.gp_infer.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
+    L.gp_run_stage.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    L.gp_tensor_shape.argtypes = [c_void_p, c_char_p, POINTER(c_int64)]
+    L.gp_read_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
+    L.gp_write_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
+    L.gp_plan_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                               POINTER(c_double)]
+    L.gp_profile_ops.argtypes = [c_void_p, c_int, c_void_p]
+    L.gp_op_info.argtypes = [c_void_p, c_int64, c_char_p, c_size_t, POINTER(c_double), POINTER(c_double),
+                             POINTER(c_double)]
+    L.gp_conv2d.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                            c_void_p, c_int, c_void_p, c_int, c_void_p]
+    L.gp_groupnorm.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                               c_int, c_void_p, c_void_p]
+    L.gp_layernorm.argtypes = [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]
+    L.gp_attention.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                               c_void_p]
+    L.gp_bilinear_up2x.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.gp_bench_conv.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double),
+                                POINTER(c_double)]
+    _lib = L
+    return L
+
+
+def _gp_dtype(t):
+    return {torch.float32: GP_F32, torch.float16: GP_F16, torch.bfloat16: GP_BF16, torch.uint8: GP_U8}[t]
+
+
+def _stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_free(st, what):
+    if st != 0:
+        raise RuntimeError(f"{what} failed: {_STATUS.get(st, st)} (see stderr)")
+
+
+class Engine:
+    """One engine per (process, GPU).  Mirrors the C-ABI one to one."""
+
+    def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("genpercept_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.L = lib()
+        self.torch_dtype = dtype
+        self.readout = readout
+        self.device = torch.device("cuda", device)
+        cfg = _Config(device, _gp_dtype(dtype), GP_READOUT_DPT if readout == "dpt" else GP_READOUT_VAE, timestep,
+                      1 if cuda_graph else 0)
+        self.h = c_void_p()
+        st = self.L.gp_create(byref(cfg), byref(self.h))
+        if st != 0:
+            raise RuntimeError(f"gp_create failed: {_STATUS.get(st, st)} (no sm_100a device?)")
+        self.plan_shape = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st, what):
+        if st != 0:
+            msg = self.L.gp_last_error(self.h).decode()
+            raise RuntimeError(f"{what}: {_STATUS.get(st, st)}: {msg}")
+
+    def load_state(self, component, sd):
+        """component in {unet, vae, dpt}; sd: {diffusers key: tensor}."""
+        for k, v in sd.items():
+            t = v.detach().to("cpu")
+            if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                t = t.float()
+            t = t.contiguous()
+            shape = (c_int64 * t.dim())(*t.shape)
+            self._ck(self.L.gp_load_tensor(self.h, f"{component}.{k}".encode(), c_void_p(t.data_ptr()),
+                                           _gp_dtype(t.dtype), shape, t.dim()), f"gp_load_tensor({k})")
+
+    def set_text_embed(self, embed):
+        e = torch.as_tensor(embed).detach().float().cpu().reshape(-1, 1024).contiguous()
+        self._ck(self.L.gp_set_text_embed(self.h, c_void_p(e.data_ptr()), e.shape[0], 1024), "gp_set_text_embed")
+
+    def finalize(self):
+        self._ck(self.L.gp_finalize(self.h), "gp_finalize")
+
+    def plan(self, batch, height, width):
+        self._ck(self.L.gp_plan(self.h, batch, height, width), "gp_plan")
+        self.plan_shape = (batch, height, width)
+
+    def infer(self, rgb, out_channels=1, out=None):
+        """rgb: [B,3,H,W] uint8 (0..255) or float16/float32 in [-1,1]; cuda or cpu tensor.
+        Returns fp32 [B,C,H,W] in [0,1] on the device of `out` (default: cuda)."""
+        assert rgb.dim() == 4 and rgb.shape[1] == 3
+        B, _, H, W = rgb.shape
+        if self.plan_shape != (B, H, W):
+            self.plan(B, H, W)
+        if rgb.dtype == torch.bfloat16:
+            rgb = rgb.float()
+        rgb = rgb.contiguous()
+        C = 1 if self.readout == "dpt" else out_channels
+        if out is None:
+            out = torch.empty((B, C, H, W), dtype=torch.float32, device=self.device)
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, C, H, W)
+        self._ck(self.L.gp_infer(self.h, c_void_p(rgb.data_ptr()), _gp_dtype(rgb.dtype), 0 if rgb.is_cuda else 1,
+                                 c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, C, _stream_ptr()), "gp_infer")
+        return out
+
+    def run_stage(self, stage, out_channels=1):
+        self._ck(self.L.gp_run_stage(self.h, stage, out_channels, _stream_ptr()), "gp_run_stage")
+
+    def tensor_shape(self, name):
+        s = (c_int64 * 4)()
+        self._ck(self.L.gp_tensor_shape(self.h, name.encode(), s), f"gp_tensor_shape({name})")
+        return tuple(int(x) for x in s)
+
+    def read_tensor(self, name):
+        shape = self.tensor_shape(name)
+        a = np.empty(shape, dtype=np.float32)
+        self._ck(self.L.gp_read_tensor(self.h, name.encode(), a.ctypes.data_as(c_void_p), a.size), "gp_read_tensor")
+        return a
+
+    def write_tensor(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        self._ck(self.L.gp_write_tensor(self.h, name.encode(), a.ctypes.data_as(c_void_p), a.size), "gp_write_tensor")
+
+    def plan_info(self):
+        n_ops, n_l, ab, wb, fl = c_int64(), c_int64(), c_int64(), c_int64(), c_double()
+        self._ck(self.L.gp_plan_info(self.h, byref(n_ops), byref(n_l), byref(ab), byref(wb), byref(fl)), "gp_plan_info")
+        return {"ops": n_ops.value, "launches": n_l.value, "arena_bytes": ab.value, "weight_bytes": wb.value,
+                "flops": fl.value}
+
+    def profile_ops(self, out_channels=1):
+        self._ck(self.L.gp_profile_ops(self.h, out_channels, _stream_ptr()), "gp_profile_ops")
+        res = []
+        buf = ctypes.create_string_buffer(256)
+        us, fl, by = c_double(), c_double(), c_double()
+        for i in range(self.plan_info()["ops"]):
+            self._ck(self.L.gp_op_info(self.h, i, buf, 256, byref(us), byref(fl), byref(by)), "gp_op_info")
+            res.append({"name": buf.value.decode(), "usec": us.value, "flops": fl.value, "bytes": by.value})
+        return res
+
+
+# ---------------------------------------------------------------- per-kernel entry points (tests)
+def _nhwc(x):
+    """NCHW torch tensor -> contiguous NHWC (same dtype)."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def conv2d(x_nhwc, w, bias=None, mode=0, residual=None, relu=False, direct=False):
+    """x_nhwc: cuda [N,H,W,Cin] f16/bf16; w: cpu fp32 [Cout,Cin,ks,ks]. Returns NHWC."""
+    N, H, W, Cin = x_nhwc.shape
+    Cout, _, ks, _ = w.shape
+    Ho, Wo = H, W
+    if mode == 1:
+        Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    elif mode == 2:
+        Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+    elif mode == 3:
+        Ho, Wo = 2 * H, 2 * W
+    y = torch.zeros((N, Ho, Wo, Cout), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    w = w.detach().float().cpu().contiguous()
+    b = bias.detach().float().cpu().contiguous() if bias is not None else None
+    st = lib().gp_conv2d(_gp_dtype(x_nhwc.dtype), c_void_p(x_nhwc.data_ptr()), N, H, W, Cin, c_void_p(w.data_ptr()),
+                         c_void_p(b.data_ptr()) if b is not None else None, Cout, ks, mode,
+                         c_void_p(residual.data_ptr()) if residual is not None else None, 1 if relu else 0,
+                         c_void_p(y.data_ptr()), 1 if direct else 0, _stream_ptr())
+    _check_free(st, "gp_conv2d")
+    return y
+
+
+def groupnorm(x_nhwc, groups, gamma, beta, eps, silu):
+    N, H, W, C = x_nhwc.shape
+    y = torch.empty_like(x_nhwc)
+    g = gamma.detach().float().cpu().contiguous()
+    b = beta.detach().float().cpu().contiguous()
+    st = lib().gp_groupnorm(_gp_dtype(x_nhwc.dtype), c_void_p(x_nhwc.data_ptr()), N, H, W, C, groups,
+                            c_void_p(g.data_ptr()), c_void_p(b.data_ptr()), eps, 1 if silu else 0,
+                            c_void_p(y.data_ptr()), _stream_ptr())
+    _check_free(st, "gp_groupnorm")
+    return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    g = gamma.detach().float().cpu().contiguous()
+    b = beta.detach().float().cpu().contiguous()
+    st = lib().gp_layernorm(_gp_dtype(x.dtype), c_void_p(x.data_ptr()), x.numel() // C, C, c_void_p(g.data_ptr()),
+                            c_void_p(b.data_ptr()), eps, c_void_p(y.data_ptr()), _stream_ptr())
+    _check_free(st, "gp_layernorm")
+    return y
+
+
+def attention(q, k, v, heads, scale):
+    """q,k,v: cuda [B,T,heads*d]."""
+    B, T, C = q.shape
+    o = torch.zeros_like(q)
+    st = lib().gp_attention(_gp_dtype(q.dtype), c_void_p(q.data_ptr()), c_void_p(k.data_ptr()), c_void_p(v.data_ptr()),
+                            B, T, heads, C // heads, scale, c_void_p(o.data_ptr()), _stream_ptr())
+    _check_free(st, "gp_attention")
+    return o
+
+
+def bilinear_up2x(x_nhwc):
+    N, H, W, C = x_nhwc.shape
+    y = torch.empty((N, 2 * H, 2 * W, C), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    st = lib().gp_bilinear_up2x(_gp_dtype(x_nhwc.dtype), c_void_p(x_nhwc.data_ptr()), N, H, W, C,
+                                c_void_p(y.data_ptr()), _stream_ptr())
+    _check_free(st, "gp_bilinear_up2x")
+    return y
+
+
+def bench_conv(dtype, N, H, W, Cin, Cout, ks=3, mode=0, iters=10):
+    us, fl = c_double(), c_double()
+    st = lib().gp_bench_conv(_gp_dtype(dtype), N, H, W, Cin, Cout, ks, mode, iters, byref(us), byref(fl))
+    _check_free(st, "gp_bench_conv")
+    return us.value, fl.value

@@ -1,0 +1,115 @@
+/* genpercept_b200 — C-ABI of the B200-native one-step perception engine.
+ *
+ * This is the drop-in boundary for the hot path of aim-uofa/GenPercept:
+ *   GenPerceptPipeline.single_infer        /root/reference/genpercept/genpercept_pipeline.py:375-486
+ *     encode_rgb  (vae.encoder, quant_conv, mean * 0.18215)                     :488-505
+ *     unet(pred_latent, t=1, empty-text embed) + DDIM(beta=1) step == -v       :443-465
+ *     decode_pred (/0.18215, post_quant_conv, vae.decoder, channel mean)       :507-526
+ *     clip(-1,1), (x+1)/2                                                      :470-472
+ *     or the DPT readout (customized_head on multi_level_feats, min-max)       :475-482
+ * Everything below the boundary is hand-written sm_100a CUDA; there is no CPU fallback: every
+ * entry point returns GP_ERR_CUDA when no CUDA device / kernel image is available.
+ *
+ * Plain C types only.  Device pointers are raw CUdeviceptr-compatible addresses (e.g.
+ * torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef GENPERCEPT_B200_H
+#define GENPERCEPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gp_engine gp_engine;
+
+typedef enum {
+  GP_OK = 0,
+  GP_ERR_INVALID = 1,   /* bad argument / shape (reference: Python assert / ValueError) */
+  GP_ERR_MISSING = 2,   /* a checkpoint tensor required by the topology was never loaded  */
+  GP_ERR_NO_PLAN = 3,   /* gp_infer before gp_plan for this (B,H,W)                        */
+  GP_ERR_CUDA = 4,      /* CUDA error (sticky: the engine is poisoned)                      */
+  GP_ERR_STATE = 5      /* call order (e.g. gp_plan before gp_finalize)                     */
+} gp_status;
+
+typedef enum { GP_F32 = 0, GP_F16 = 1, GP_BF16 = 2, GP_U8 = 3 } gp_dtype;
+typedef enum { GP_READOUT_VAE = 0, GP_READOUT_DPT = 1 } gp_readout;
+
+typedef struct {
+  int device;            /* CUDA device ordinal                                             */
+  int dtype;             /* GP_F16 or GP_BF16: storage / tensor-core operand type            */
+  int readout;           /* gp_readout: VAE decoder (run.py default) or DPT head (:296-301)  */
+  int timestep;          /* UNet timestep; 1 for GenPercept (ddim.py + scheduler beta=1), or
+                            the reference's --fix_timesteps value                           */
+  int use_cuda_graph;    /* capture the planned op list into one CUDA graph                  */
+} gp_config;
+
+/* replaces: GenPerceptPipeline.__init__/from_pretrained model assembly (run.py:314-376) */
+gp_status gp_create(const gp_config* cfg, gp_engine** out);
+void gp_destroy(gp_engine* e);
+const char* gp_last_error(gp_engine* e);
+
+/* replaces: load_state_dict of the diffusers-format checkpoints (run.py:336-357, :296-312).
+ * `key` = "<component>.<diffusers key>", component in {unet, vae, dpt}.  Host pointer, copied. */
+gp_status gp_load_tensor(gp_engine* e, const char* key, const void* host_ptr, int dtype,
+                         const int64_t* shape, int ndim);
+/* replaces: encode_text()'s cached self.text_embed (genpercept_pipeline.py:360-372, :425-429).
+ * fp32 [n_tokens, dim]; the engine's closed-form cross-attention requires n_tokens == 2. */
+gp_status gp_set_text_embed(gp_engine* e, const float* host_ptr, int n_tokens, int dim);
+/* folds constants, re-packs weights K-major 16-bit, uploads. */
+gp_status gp_finalize(gp_engine* e);
+
+/* builds the static op list, activation arena and (optionally) CUDA graph for one input shape. */
+gp_status gp_plan(gp_engine* e, int batch, int height, int width);
+
+/* replaces: single_infer.  rgb: [B,3,H,W] NCHW, device (or pinned/pageable host if
+ * rgb_on_host != 0; copied on `stream`), dtype GP_U8 (0..255, mapped x/255*2-1 as
+ * genpercept_pipeline.py:245) or GP_F16/GP_F32 already in [-1,1].
+ * out: fp32 [B,C,H,W] in [0,1], C = out_channels (1: channel-mean modes depth/matting/dis/
+ * disparity :523-525; 3: normal/seg); device, or host if out_on_host != 0.  Asynchronous on
+ * `stream` unless a host buffer is involved, in which case it returns after the copy. */
+gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, float* out,
+                   int out_on_host, int out_channels, void* stream);
+
+/* Stage entry points for parity tests (each runs a contiguous slice of the planned op list). */
+typedef enum { GP_STAGE_PRE = 0, GP_STAGE_VAE_ENCODE = 1, GP_STAGE_UNET = 2, GP_STAGE_READOUT = 3 } gp_stage;
+gp_status gp_run_stage(gp_engine* e, int stage, int out_channels, void* stream);
+/* Named internal tensors kept alive by the plan: "rgb", "rgb_latent", "z" (decoder input =
+ * post_quant_conv(-unet_out/0.18215)), "feat0".."feat3" (DPT taps), "out".  fp32 NCHW on host. */
+gp_status gp_tensor_shape(gp_engine* e, const char* name, int64_t shape[4]);
+gp_status gp_read_tensor(gp_engine* e, const char* name, float* host_out, size_t capacity_elems);
+gp_status gp_write_tensor(gp_engine* e, const char* name, const float* host_in, size_t elems);
+
+/* Introspection for bench.py */
+gp_status gp_plan_info(gp_engine* e, int64_t* n_ops, int64_t* n_kernel_launches, int64_t* arena_bytes,
+                       int64_t* weight_bytes, double* igemm_flops);
+/* name/us of the i-th op after gp_profile_ops ran the plan once with CUDA events per op. */
+gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream);
+gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops,
+                     double* bytes);
+
+/* ---- per-kernel entry points (parity tests, micro-benchmarks); all pointers are device ---- */
+/* 3x3 / 1x1 convolution through the tcgen05 implicit-GEMM kernel.  x: 16-bit NHWC [N,H,W,Cin];
+ * w: fp32 [Cout,Cin,ks,ks] (host); mode: 0 stride-1 pad ks/2, 1 stride-2 pad (1,1,1,1),
+ * 2 stride-2 pad (0,1,0,1) (VAE encoder), 3 nearest-2x upsample then stride-1.  y: 16-bit NHWC. */
+gp_status gp_conv2d(int dtype, const void* x, int N, int H, int W, int Cin, const float* w_host,
+                    const float* bias_host, int Cout, int ks, int mode, const void* residual, int relu,
+                    void* y, int use_direct_kernel, void* stream);
+gp_status gp_groupnorm(int dtype, const void* x, int N, int H, int W, int C, int groups, const float* gamma_host,
+                       const float* beta_host, float eps, int silu, void* y, void* stream);
+gp_status gp_layernorm(int dtype, const void* x, int64_t tokens, int C, const float* gamma_host,
+                       const float* beta_host, float eps, void* y, void* stream);
+/* softmax(q k^T * scale) v per (batch, head); q,k,v,o: 16-bit [B,T,heads*d] */
+gp_status gp_attention(int dtype, const void* q, const void* k, const void* v, int B, int T, int heads, int d,
+                       float scale, void* o, void* stream);
+gp_status gp_bilinear_up2x(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
+/* time one igemm configuration: returns average microseconds over `iters` launches */
+gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int ks, int mode, int iters,
+                        double* usec, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
