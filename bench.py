@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the GenPercept one-step hot path (BASELINE.json metric: images/sec at 768x768 depth).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of ``GenPerceptPipeline.single_infer`` over one batch of 8 synthetic 768x768
+images per GPU (BASELINE.json configs[1]; weak scaling: every rank runs its own batch, no data-path
+collective).  Rank 0 prints ONE JSON line:
+
+  value        whole-job images/sec with the uint8 batch already resident in HBM (device timed).
+  e2e          the same metric through the public API with pinned HOST buffers: H2D of the uint8
+               batch and D2H of the fp32 maps inside the timed region.
+  roofline     the dominant kernel (tcgen05 implicit GEMM): algorithmic FLOPs of all its launches in
+               a step / their summed CUDA-event durations, vs the measured bf16 peak.
+  cpu_baseline the CPU oracle (oracle/, a port of the diffusers path) on the host cores, bounded sample.
+
+--impl reference times the reference's own CPU path.  diffusers is not installable here (no
+network, absent from /opt/wheelhouse), so that arm runs the oracle port with all host threads;
+each step is a bounded sample (one 256x256 image) scaled to 768x768 images by algorithmic FLOPs.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from genpercept_b200 import flops as FL  # noqa: E402
+from genpercept_b200 import weights as W  # noqa: E402
+
+METRIC = "images/sec at 768x768 depth"
+UNIT = "images/s"
+
+
+def text_embed():
+    e = np.load(os.path.join(ROOT, "tests", "golden", "empty_text_embed_2x1024.npy")).astype(np.float32)
+    return torch.from_numpy(e)[None]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", 1450.1), "tflops_burst": d.get("bf16_tflops", 1703.2),
+                "hbm_gbs": d.get("hbm_gbs", 6486.5), "src": "MEASURED_PEAKS.json (sustained bf16 GEMM; kernel timed inside a long step)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_sample(state, res, threads, steps=1, warmup=0):
+    """Oracle (CPU port of the diffusers path) on `res` x `res`, 1 image per step."""
+    from oracle.pipeline import OraclePipeline
+    torch.set_num_threads(threads)
+    p = OraclePipeline(state, text_embed())
+    g = torch.Generator().manual_seed(1002)
+    x = torch.randint(0, 256, (1, 3, res, res), generator=g, dtype=torch.uint8).float() / 255.0 * 2.0 - 1.0
+    for _ in range(warmup):
+        p.single_infer(x, mode="depth")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        p.single_infer(x, mode="depth")
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    res = args.ref_res
+    state = W.synth_state(1234, with_dpt=False)
+    sec = cpu_baseline_sample(state, res, cores, steps=args.steps, warmup=args.warmup)
+    scale = FL.single_infer_flops(768, 768) / FL.single_infer_flops(res, res)
+    v = 1.0 / (sec * scale)
+    sample = (f"each step = single_infer on 1 image {res}x{res} fp32 (oracle port of the diffusers CPU path, "
+              f"{cores} threads); value = measured img/s / {scale:.2f} (768x768 : {res}x{res} algorithmic FLOPs)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1000.0, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "depth 768x768 (BASELINE.json configs[1]), CPU reference arm", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--res", type=int, default=768)
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
+    ap.add_argument("--readout", default="vae", choices=["vae", "dpt"])
+    ap.add_argument("--gather", action="store_true", help="all-gather the maps over NCCL inside the e2e step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-res", type=int, default=256)
+    ap.add_argument("--cuda-graph", action="store_true")
+    ap.add_argument("--ops-json", default=None, help="write the per-op timing table here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from genpercept_b200.pipeline import GenPerceptPipeline
+
+    dt = torch.float16 if args.dtype == "f16" else torch.bfloat16
+    state = W.synth_state(1234, with_dpt=args.readout == "dpt")
+    pipe = GenPerceptPipeline(unet=state["unet"], vae=state["vae"],
+                              customized_head=state["dpt"] if args.readout == "dpt" else None,
+                              text_embed=text_embed(), torch_dtype=dt, device=local, cuda_graph=args.cuda_graph)
+    eng = pipe._engine
+    B, R = args.batch, args.res
+    g = torch.Generator().manual_seed(1002 + rank)
+    host_in = [torch.randint(0, 256, (B, 3, R, R), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dev_in = [h.cuda() for h in host_in]
+    dev_out = torch.empty((B, 1, R, R), dtype=torch.float32, device="cuda")
+    host_out = torch.empty((B, 1, R, R), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * B, 1, R, R), dtype=torch.float32, device="cuda") if (args.gather and world > 1) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        pipe.single_infer(dev_in[i % 2], mode="depth")
+        eng.infer(host_in[i % 2], out_channels=1, out=host_out)
+    info = eng.plan_info()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- device-resident timing (value)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        eng.infer(dev_in[i % 2], out_channels=1, out=dev_out)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    # ---- end-to-end through the public API with host buffers (e2e)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        pred = pipe.single_infer(host_in[i % 2], mode="depth")          # H2D inside gp_infer
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered, pred)
+        host_out.copy_(pred, non_blocking=True)                         # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-op pass: CUDA events around every op of one step (serialised, warm), rank 0 only
+    roofline = None
+    if rank == 0:
+        ops = eng.profile_ops(out_channels=1)
+        ops = eng.profile_ops(out_channels=1)
+        ig = [o for o in ops if o["kind"] == 1 and o["usec"] > 0]
+        t_ig = sum(o["usec"] for o in ig) * 1e-6
+        f_ig = sum(o["flops"] for o in ig)
+        t_all = sum(o["usec"] for o in ops) * 1e-6
+        pk = measured_peaks()
+        ach = f_ig / t_ig / 1e12 if t_ig > 0 else 0.0
+        roofline = {"kernel": "gp::igemm_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                    "launches_per_step": len(ig), "share_of_step_time": t_ig / t_all if t_all > 0 else None,
+                    "peak_source": pk["src"],
+                    "how": "sum(algorithmic FLOPs of every igemm launch in a step) / sum(CUDA-event duration of "
+                           "those launches), one extra warm step with events around each op on the launch stream"}
+        if args.ops_json:
+            json.dump(ops, open(args.ops_json, "w"), indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sec = cpu_baseline_sample(state, args.ref_res, cores, steps=1, warmup=1)
+        scale = FL.single_infer_flops(R, R) / FL.single_infer_flops(args.ref_res, args.ref_res)
+        cpu = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle (CPU port of the diffusers path, fp32, {cores} threads): 1 image {args.ref_res}x"
+                         f"{args.ref_res} in {sec:.2f} s, scaled by {scale:.2f} ({R}x{R} : {args.ref_res}x{args.ref_res} "
+                         "algorithmic FLOPs)"}
+
+    if rank == 0:
+        n_img = world * B * args.steps
+        per_img = FL.single_infer_flops(R, R, args.readout)
+        out = {
+            "metric": METRIC, "value": n_img / (ms_dev / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"depth {R}x{R} batch={B}/GPU, {args.readout} readout (BASELINE.json configs[1])",
+                       "weights": "seeded synthetic SD-2.1 topology (no checkpoints offline)",
+                       "global_batch": world * B, "parallelism": f"dp{world} (independent replicas, batch sharded)",
+                       "l2": f"no flush needed: per-step working set {info['arena_bytes'] / 2**30:.1f} GiB arena + "
+                             f"{info['weight_bytes'] / 2**30:.2f} GiB weights >> 126 MB L2; 2 alternating inputs",
+                       "algorithmic_tflop_per_image": per_img / 1e12, "cuda_graph": bool(args.cuda_graph)},
+            "model_tflops": n_img * per_img / (ms_dev / 1000.0) / 1e12,
+            "e2e": {"value": n_img / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": B * 3 * R * R,
+                    "d2h_bytes_per_step": B * R * R * 4, "ms_per_step": ms_e2e / args.steps,
+                    "api": "GenPerceptPipeline.single_infer(pinned uint8 host batch) + D2H of the fp32 maps"},
+            "gpu_launches": int(info["launches"]) * args.steps * world,   # kernels launched in the device-timed region
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -239,6 +239,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
                                               std::to_string(p.nkb[c] * 64) + ")");
   GP_REQUIRE(a.w->rows >= Cout || a.w->rows == Cout, name + ": packed rows < Cout");
   push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
+  ops.back().kind = 1;
 }
 
 void Builder::attention_qkv(const std::string& name, const void* q, const void* k, long long cs, const void* vT, int B,
@@ -271,6 +272,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       finalize_or_throw(&p, name + ".qk");
       push(name + ".qk", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
            [p](cudaStream_t s) { return igemm_launch(p, s); });
+      ops.back().kind = 1;
     }
     {
       const long long rows = (long long)B * heads * T;
@@ -300,6 +302,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       finalize_or_throw(&p, name + ".pv");
       push(name + ".pv", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
            [p](cudaStream_t s) { return igemm_launch(p, s); });
+      ops.back().kind = 1;
     }
   }
   arena_.release(s_off);
@@ -339,6 +342,7 @@ void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk
     finalize_or_throw(&p, name + ".to_vT");
     push(name + ".to_vT", 1, 2.0 * B * (double)T * C * C, (double)vt_bytes + (double)l.bytes(),
          [p](cudaStream_t s) { return igemm_launch(p, s); });
+    ops.back().kind = 1;
   }
   const uint16_t* qp = measuring_ ? nullptr : reinterpret_cast<const uint16_t*>(ptr(qk));
   attention_qkv(name, qp, qp ? qp + C : nullptr, 2 * C, measuring_ ? nullptr : raw_ptr(vt_off), B, T, heads, d, pv_bias, out);

@@ -1090,7 +1090,8 @@ gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream) {
   });
 }
 
-gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops, double* bytes) {
+gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops, double* bytes,
+                     int* kind) {
   return guarded(e, [&]() {
     Plan* p = e->cur;
     if (!p) throw GpError(GP_ERR_NO_PLAN, "no plan");
@@ -1100,6 +1101,7 @@ gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, d
     if (usec) *usec = op.usec;
     if (flops) *flops = op.flops;
     if (bytes) *bytes = op.bytes;
+    if (kind) *kind = op.kind;
   });
 }
 

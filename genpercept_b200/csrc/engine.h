@@ -77,6 +77,7 @@ struct Op {
   int stage = 0;
   int variant = 0;            // 0: always; 1 / 3: only when out_channels matches
   int launches = 1;
+  int kind = 0;               // 1: tcgen05 implicit-GEMM launch, 0: anything else
   double flops = 0, bytes = 0;
   float usec = 0;
   std::function<cudaError_t(cudaStream_t)> run;

@@ -56,7 +56,7 @@ def lib():
                                POINTER(c_double)]
     L.gp_profile_ops.argtypes = [c_void_p, c_int, c_void_p]
     L.gp_op_info.argtypes = [c_void_p, c_int64, c_char_p, c_size_t, POINTER(c_double), POINTER(c_double),
-                             POINTER(c_double)]
+                             POINTER(c_double), POINTER(c_int)]
     L.gp_conv2d.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_int, c_void_p]
     L.gp_groupnorm.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
@@ -186,10 +186,11 @@ class Engine:
         self._ck(self.L.gp_profile_ops(self.h, out_channels, _stream_ptr()), "gp_profile_ops")
         res = []
         buf = ctypes.create_string_buffer(256)
-        us, fl, by = c_double(), c_double(), c_double()
+        us, fl, by, kd = c_double(), c_double(), c_double(), c_int()
         for i in range(self.plan_info()["ops"]):
-            self._ck(self.L.gp_op_info(self.h, i, buf, 256, byref(us), byref(fl), byref(by)), "gp_op_info")
-            res.append({"name": buf.value.decode(), "usec": us.value, "flops": fl.value, "bytes": by.value})
+            self._ck(self.L.gp_op_info(self.h, i, buf, 256, byref(us), byref(fl), byref(by), byref(kd)), "gp_op_info")
+            res.append({"name": buf.value.decode(), "usec": us.value, "flops": fl.value, "bytes": by.value,
+                        "kind": kd.value})
         return res
 
 

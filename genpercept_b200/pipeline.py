@@ -1,0 +1,270 @@
+"""Drop-in for ``genpercept.GenPerceptPipeline`` / ``GenPerceptOutput``
+(/root/reference/genpercept/genpercept_pipeline.py:50-62, :64-526) on top of the native engine.
+
+Same constructor kwargs, ``__call__`` kwargs/defaults (:146-162), helper methods
+(``single_infer`` :375, ``encode_rgb`` :488, ``decode_pred`` :507, ``encode_text`` :360) and error
+behaviour (asserts / TypeError / ValueError at the same points).  Below this file nothing is
+PyTorch: ``single_infer`` is one ``gp_infer`` call into libgenpercept_b200.so.
+
+Extensions: ``input_image`` may be a uint8 tensor [B,3,H,W] with B > 1 (the
+reference's ``expand(ensemble_size)`` admits only B == 1); outputs then carry a leading batch dim.
+Multi-GPU: ``genpercept_b200.parallel.sharded_infer`` shards the batch over ranks.
+"""
+import logging
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional, Union
+
+import numpy as np
+import torch
+from PIL import Image
+from torchvision.transforms.functional import pil_to_tensor, resize
+
+from . import weights as W
+from .engine import Engine
+from .image_util import chw2hwc, colorize_depth_maps, get_tv_resample_method, resize_max_res
+
+ONE_CHANNEL_MODES = ("depth", "matting", "dis", "disparity")     # genpercept_pipeline.py:523
+
+
+@dataclass
+class GenPerceptOutput:
+    """pred_np: result in [0,1]; pred_colored: PIL image or None (genpercept_pipeline.py:50-62)."""
+    pred_np: np.ndarray
+    pred_colored: Union[None, Image.Image, list]
+
+    def __getitem__(self, k):
+        return (self.pred_np, self.pred_colored)[k] if isinstance(k, int) else getattr(self, k)
+
+
+def _as_state_dict(m):
+    """Accept a module (anything with .state_dict()), a dict, or a path to a checkpoint file/dir."""
+    if m is None:
+        return None
+    if isinstance(m, dict):
+        return m
+    if isinstance(m, (str, os.PathLike)):
+        return load_checkpoint(m)
+    if hasattr(m, "state_dict"):
+        return m.state_dict()
+    raise TypeError(f"cannot take weights from {type(m)}")
+
+
+def load_checkpoint(path):
+    """diffusers folder layouts the reference reads (run.py:283-343): a dir holding
+    diffusion_pytorch_model.{safetensors,bin} / model.safetensors, or such a file directly."""
+    path = str(path)
+    if os.path.isdir(path):
+        for n in ("diffusion_pytorch_model.safetensors", "model.safetensors", "diffusion_pytorch_model.bin"):
+            if os.path.exists(os.path.join(path, n)):
+                path = os.path.join(path, n)
+                break
+        else:
+            raise FileNotFoundError(f"no checkpoint file under {path}")
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu")
+
+
+class GenPerceptPipeline:
+    latent_scale_factor = 0.18215                                 # genpercept_pipeline.py:96
+
+    def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None,
+                 default_denoising_steps: Optional[int] = 10, default_processing_resolution: Optional[int] = 768,
+                 rgb_blending=False, customized_head=None, genpercept_pipeline=True, *, text_embed=None,
+                 torch_dtype=torch.float16, device=0, cuda_graph=False, fix_timesteps=None):
+        self.genpercept_pipeline = genpercept_pipeline
+        if not genpercept_pipeline:
+            raise NotImplementedError("only the one-step GenPercept mode (genpercept_pipeline=True) is built; "
+                                      "multi-step Marigold / rgb_blending archs are SURVEY.md 8(f4)")
+        default_denoising_steps = 1
+        rgb_blending = True
+        if scheduler is not None and hasattr(scheduler, "beta_start"):
+            assert scheduler.beta_start == 1 and scheduler.beta_end == 1, \
+                "the one-step collapse x0 = -v needs the beta=1 scheduler (hf_configs/scheduler_beta_1.0_1.0)"
+        self.scheduler = scheduler
+        self.text_encoder = text_encoder
+        self.tokenizer = tokenizer
+        self.default_denoising_steps = default_denoising_steps
+        self.default_processing_resolution = default_processing_resolution
+        self.rgb_blending = rgb_blending
+        self.customized_head = customized_head
+        self.text_embed = None
+        self.dtype = torch.float32 if torch_dtype is None else torch_dtype
+        if self.dtype == torch.float32:
+            logging.warning("genpercept_b200 computes in 16-bit storage / fp32 accumulate; using float16")
+            self.dtype = torch.float16
+        self._timestep = int(fix_timesteps) if fix_timesteps else 1
+        self._engine = Engine(dtype=self.dtype, readout="dpt" if customized_head is not None else "vae",
+                              timestep=self._timestep, device=device, cuda_graph=cuda_graph)
+        self.device = self._engine.device
+        unet_sd = dict(_as_state_dict(unet))
+        vae_sd = W.remap_legacy_vae_keys(_as_state_dict(vae))
+        if customized_head is not None:          # run.py:322-331 drops these for the DPT readout
+            unet_sd = {k: v for k, v in unet_sd.items() if not k.startswith(("conv_out", "conv_norm_out"))}
+            self._engine.load_state("dpt", _as_state_dict(customized_head))
+        self._engine.load_state("unet", unet_sd)
+        self._engine.load_state("vae", vae_sd)
+        self._finalized = False
+        if text_embed is not None:
+            self._set_text_embed(text_embed)
+
+    # ------------------------------------------------------------------ diffusers-pipeline surface
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, variant=None, torch_dtype=None, **kw):
+        """Mirrors ``GenPerceptPipeline.from_pretrained(sd21_dir, variant=…, torch_dtype=…,
+        genpercept_pipeline=True, unet=…, scheduler=…, [customized_head|vae]=…)`` (run.py:374-376):
+        vae / text_encoder / tokenizer come from the SD-2.1 folder unless passed."""
+        root = str(pretrained_model_name_or_path)
+        if kw.get("vae") is None:
+            kw["vae"] = os.path.join(root, "vae")
+        if kw.get("unet") is None:
+            kw["unet"] = os.path.join(root, "unet")
+        if kw.get("text_embed") is None and kw.get("text_encoder") is None and os.path.isdir(os.path.join(root, "text_encoder")):
+            from transformers import CLIPTextModel, CLIPTokenizer
+            kw["text_encoder"] = CLIPTextModel.from_pretrained(os.path.join(root, "text_encoder"))
+            kw["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
+        return cls(torch_dtype=torch_dtype, **kw)
+
+    def to(self, *a, **k):
+        return self
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):   # run.py:382-385 calls this in a try
+        return None
+
+    def set_progress_bar_config(self, **k):
+        return None
+
+    # ------------------------------------------------------------------ text embedding
+    def _set_text_embed(self, e):
+        e = torch.as_tensor(e).detach().float().cpu().reshape(1, -1, 1024)
+        if self._finalized:
+            raise RuntimeError("the text embedding is folded into the weights at first use; build a new pipeline")
+        self.text_embed = e.to(self.dtype)
+        self._engine.set_text_embed(e)
+
+    def encode_text(self, prompt):
+        """genpercept_pipeline.py:360-372: tokenizer(prompt, padding='do_not_pad') -> CLIP -> [1,2,1024]."""
+        if self.text_encoder is None or self.tokenizer is None:
+            raise RuntimeError("no text_encoder/tokenizer given: pass text_embed= (e.g. the fixture "
+                               "tests/golden/empty_text_embed_2x1024.npy)")
+        ti = self.tokenizer(prompt, padding="do_not_pad", max_length=self.tokenizer.model_max_length,
+                            truncation=True, return_tensors="pt")
+        with torch.no_grad():
+            self._set_text_embed(self.text_encoder(ti.input_ids)[0])
+
+    def _ensure_ready(self, prompt=""):
+        if self.text_embed is None:
+            self.encode_text(prompt)
+        if not self._finalized:
+            self._engine.finalize()
+            self._finalized = True
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def single_infer(self, rgb_in, num_inference_steps=1, generator=None, show_pbar=False, fix_timesteps=None,
+                     prompt="", mode=None):
+        """rgb_in: [B,3,H,W] uint8 (0..255) or float in [-1,1].  Returns fp32 [B,1|3,H,W] in [0,1] (cuda)."""
+        if fix_timesteps and int(fix_timesteps) != self._timestep:
+            raise ValueError("fix_timesteps is a per-pipeline constant here (folded into the ResNet biases): "
+                             "construct GenPerceptPipeline(..., fix_timesteps=t)")
+        assert num_inference_steps == 1, "GenPercept only forward once."
+        self._ensure_ready(prompt)
+        mode = mode or getattr(self, "mode", None)
+        ch = 1 if (self.customized_head is not None or mode in ONE_CHANNEL_MODES) else 3
+        return self._engine.infer(rgb_in, out_channels=ch)
+
+    @torch.no_grad()
+    def encode_rgb(self, rgb_in):
+        from . import engine as E
+        self._ensure_ready()
+        B, _, H, W = rgb_in.shape
+        self._engine.plan(B, H, W)
+        x = rgb_in if rgb_in.dtype == torch.uint8 else rgb_in.float()
+        # PRE is part of gp_infer; reuse it by running a full preprocess through write_tensor
+        if x.dtype == torch.uint8:
+            x = x.float() / 255.0 * 2.0 - 1.0
+        self._engine.write_tensor("rgb", x.cpu().numpy())
+        self._engine.run_stage(E.STAGE_VAE_ENCODE)
+        return torch.from_numpy(self._engine.read_tensor("rgb_latent")).to(self.device, self.dtype)
+
+    @torch.no_grad()
+    def decode_pred(self, pred_latent, post_quant=None):
+        """Returns the decoded map clipped to [-1,1] (the reference clips right after, :470).
+        `post_quant`=(weight[4,4], bias[4]) of vae.post_quant_conv; the engine folded it into the UNet
+        tail, so a caller decoding a *foreign* latent must supply it."""
+        from . import engine as E
+        if self.customized_head is not None:
+            raise ValueError("decode_pred is undefined for the DPT readout")
+        self._ensure_ready()
+        z = pred_latent.float().cpu() / self.latent_scale_factor
+        if post_quant is not None:
+            w, b = post_quant
+            z = torch.einsum("oc,bchw->bohw", w.float().reshape(4, 4), z) + b.float().view(1, 4, 1, 1)
+        B, _, h, w_ = z.shape
+        self._engine.plan(B, h * 8, w_ * 8)
+        self._engine.write_tensor("z", z.numpy())
+        ch = 1 if getattr(self, "mode", "depth") in ONE_CHANNEL_MODES else 3
+        self._engine.run_stage(E.STAGE_READOUT, ch)
+        out = self._engine.read_tensor("out").reshape(-1)[:B * ch * h * 8 * w_ * 8].reshape(B, ch, h * 8, w_ * 8)
+        return torch.from_numpy(out * 2.0 - 1.0).to(self.device)
+
+    @torch.no_grad()
+    def __call__(self, input_image, denoising_steps: Optional[int] = None, ensemble_size: int = 1,
+                 processing_res: Optional[int] = None, match_input_res: bool = True, resample_method: str = "bilinear",
+                 batch_size: int = 0, generator=None, color_map: str = "Spectral", show_progress_bar: bool = True,
+                 ensemble_kwargs: Dict = None, mode=None, fix_timesteps=None, prompt="") -> GenPerceptOutput:
+        assert mode is not None, "mode of GenPerceptPipeline can be chosen from ['depth', 'normal', 'seg', 'matting', 'dis']."
+        self.mode = mode
+        if denoising_steps is None:
+            denoising_steps = self.default_denoising_steps
+        if processing_res is None:
+            processing_res = self.default_processing_resolution
+        assert processing_res >= 0
+        assert ensemble_size >= 1
+        assert ensemble_size == 1
+        assert denoising_steps == 1
+        resample = get_tv_resample_method(resample_method)
+        if isinstance(input_image, Image.Image):
+            rgb = pil_to_tensor(input_image.convert("RGB")).unsqueeze(0)
+        elif isinstance(input_image, torch.Tensor):
+            rgb = input_image
+        else:
+            raise TypeError(f"Unknown input type: {type(input_image) = }")
+        input_size = rgb.shape
+        assert 4 == rgb.dim() and 3 == input_size[-3], f"Wrong input shape {input_size}, expected [1, rgb, H, W]"
+        if processing_res > 0:
+            rgb = resize_max_res(rgb, max_edge_resolution=processing_res, resample_method=resample)
+        if rgb.dtype != torch.uint8:
+            assert rgb.min() >= 0 and rgb.max() <= 255
+            rgb = rgb.round().clamp(0, 255).to(torch.uint8) if rgb.is_floating_point() else rgb.to(torch.uint8)
+        # normalisation x/255*2-1 and the cast to self.dtype (:245-246) happen inside the engine
+        pred = self.single_infer(rgb, num_inference_steps=denoising_steps, generator=generator,
+                                 show_pbar=show_progress_bar, fix_timesteps=fix_timesteps, prompt=prompt, mode=mode)
+        if match_input_res and tuple(pred.shape[-2:]) != tuple(input_size[-2:]):
+            pred = resize(pred, list(input_size[-2:]), interpolation=resample, antialias=True)
+        batched = pred.shape[0] > 1
+        pred_np = pred.cpu().numpy()
+        pred_np = pred_np.squeeze() if not batched else (pred_np[:, 0] if pred_np.shape[1] == 1 else pred_np)
+        pred_np = pred_np.clip(0, 1)
+        items = [pred_np] if not batched else list(pred_np)
+        colored = []
+        for p in items:
+            if color_map is not None:
+                assert self.mode in ["depth", "disparity"]
+                c = colorize_depth_maps(p, 0, 1, cmap=color_map).squeeze()
+                c = (c * 255).astype(np.uint8)
+                colored.append(Image.fromarray(chw2hwc(c)))
+            else:
+                c = (p * 255.0).astype(np.uint8)
+                if c.ndim == 3 and c.shape[0] == 3:
+                    c = np.transpose(c, (1, 2, 0))
+                colored.append(Image.fromarray(c))
+        if batched:
+            if pred_np.ndim == 4 and pred_np.shape[1] == 3:
+                pred_np = np.transpose(pred_np, (0, 2, 3, 1))
+            return GenPerceptOutput(pred_np=pred_np, pred_colored=colored)
+        if pred_np.ndim == 3 and pred_np.shape[0] == 3:
+            pred_np = np.transpose(pred_np, (1, 2, 0))
+        return GenPerceptOutput(pred_np=pred_np, pred_colored=colored[0])

@@ -87,8 +87,9 @@ gp_status gp_plan_info(gp_engine* e, int64_t* n_ops, int64_t* n_kernel_launches,
                        int64_t* weight_bytes, double* igemm_flops);
 /* name/us of the i-th op after gp_profile_ops ran the plan once with CUDA events per op. */
 gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream);
+/* kind: 1 = tcgen05 implicit-GEMM launch, 0 = other kernels */
 gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops,
-                     double* bytes);
+                     double* bytes, int* kind);
 
 /* ---- per-kernel entry points (parity tests, micro-benchmarks); all pointers are device ---- */
 /* 3x3 / 1x1 convolution through the tcgen05 implicit-GEMM kernel.  x: 16-bit NHWC [N,H,W,Cin];

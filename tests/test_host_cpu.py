@@ -1,0 +1,64 @@
+"""CPU tests of the host layer: C-ABI symbols, loud failure without a GPU, image helpers."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from genpercept_b200 import build, engine
+    build.build()
+    lib = engine.lib()
+    hdr = open(os.path.join(ROOT, "include", "genpercept_b200.h")).read()
+    syms = sorted(set(re.findall(r"\b(gp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    from genpercept_b200 import engine
+    cfg = engine._Config(0, engine.GP_F16, 0, 1, 0)
+    h = ctypes.c_void_p()
+    assert engine.lib().gp_create(ctypes.byref(cfg), ctypes.byref(h)) == 4      # GP_ERR_CUDA, no fallback
+    with pytest.raises(RuntimeError):
+        engine.Engine()
+
+
+def test_product_package_never_imports_oracle():
+    for dp, _, fs in os.walk(os.path.join(ROOT, "genpercept_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+
+
+def test_resize_max_res_matches_reference_semantics():
+    from genpercept_b200.image_util import get_tv_resample_method, resize_max_res
+    x = torch.randint(0, 256, (1, 3, 450, 675), dtype=torch.uint8)
+    y = resize_max_res(x, 768, get_tv_resample_method("bilinear"))
+    assert tuple(y.shape) == (1, 3, 512, 768) and y.dtype == torch.uint8      # int() truncation (image_util.py:101)
+    with pytest.raises(ValueError):
+        get_tv_resample_method("lanczos")
+
+
+def test_spectral_colormap_endpoints():
+    from genpercept_b200.image_util import colorize_depth_maps
+    c = colorize_depth_maps(np.array([[0.0, 1.0], [0.5, 0.25]]), 0, 1)
+    np.testing.assert_allclose(c[0, :, 0, 0], [158 / 255, 1 / 255, 66 / 255], atol=1e-6)
+    np.testing.assert_allclose(c[0, :, 0, 1], [94 / 255, 79 / 255, 162 / 255], atol=1e-6)
+
+
+def test_legacy_vae_key_remap():
+    from genpercept_b200.weights import remap_legacy_vae_keys
+    sd = {"encoder.mid_block.attentions.0.query.weight": torch.zeros(512, 512, 1, 1),
+          "encoder.mid_block.attentions.0.proj_attn.bias": torch.zeros(512), "encoder.conv_in.weight": torch.zeros(1)}
+    out = remap_legacy_vae_keys(sd)
+    assert out["encoder.mid_block.attentions.0.to_q.weight"].shape == (512, 512)
+    assert "encoder.mid_block.attentions.0.to_out.0.bias" in out and "encoder.conv_in.weight" in out
