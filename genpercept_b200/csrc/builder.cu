@@ -3,7 +3,10 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "engine.h"
+#include "fattn.h"
 
 namespace gp {
 
@@ -246,6 +249,25 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
                             int T, int heads, int d, const float* pv_bias, const T4& out) {
   const int Tp = ceil_div(T, 8) * 8;
   const int C = heads * d;
+  static const bool unfused = std::getenv("GP_UNFUSED_ATTN") != nullptr;
+  if (d == 64 && !unfused) {   // fused tcgen05 flash-attention kernel (S and P stay on chip)
+    if (measuring_) return;
+    FattnParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.out = ptr(out);
+    p.out_b_stride = (long long)T * C;
+    p.out_row_stride = C;
+    p.T = T; p.heads = heads; p.B = B; p.q_tiles = ceil_div(T, 128);
+    p.scale_log2e = 1.4426950408889634f;
+    p.bf16 = bf16_ ? 1 : 0;
+    check_cuda(make_tmap_b(&p.tmQ, q, C, T, B, cs, (long long)T * cs, 128, bf16_), name + ": tmap Q");
+    check_cuda(make_tmap_b(&p.tmK, k, C, T, B, cs, (long long)T * cs, 128, bf16_), name + ": tmap K");
+    check_cuda(make_tmap_b(&p.tmV, vT, T, C, B, Tp, (long long)C * Tp, 64, bf16_), name + ": tmap Vt");
+    push(name + ".fattn", 1, 4.0 * B * heads * (double)T * T * d, 4.0 * B * T * C * 2,
+         [p](cudaStream_t s) { return fattn_launch(p, s); });
+    ops.back().kind = 2;
+    return;
+  }
   const size_t s_bytes = (size_t)B * heads * T * Tp * 2;
   const size_t s_off = arena_.alloc(s_bytes);
   if (!measuring_) {

@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -365,6 +366,22 @@ struct gp_engine {
   }
 
   // ------------------------------------------------------------------ graph pieces
+  // 3x3 conv whose input is an NHWC8 tensor with `cin` (3 or 4) real channels: one 64-wide K chunk
+  // per tap through the tensor-core kernel (the TMA box zero-fills channels >= 8).  GP_DIRECT_SMALL=1
+  // routes it through the SIMT direct kernel instead (bring-up triage only).
+  void small_cin_conv(Builder& b, const std::string& key, const T4& src8, int cin, const T4& out) {
+    static const bool direct = std::getenv("GP_DIRECT_SMALL") != nullptr;
+    if (direct) {
+      b.direct(key, src8, cin, direct_w(key, cin), out, 0, nullptr, 0);
+      return;
+    }
+    ConvArgs c;
+    c.srcs = {src8};
+    c.w = &conv_w(key, {cin});
+    c.out = out;
+    b.conv(key, c);
+  }
+
   T4 resnet(Builder& b, const std::string& p, const std::vector<T4>& xs, int cout, float eps, bool temb_on) {
     int cin = 0;
     std::vector<int> cs;
@@ -491,7 +508,7 @@ struct gp_engine {
   T4 vae_encoder(Builder& b, const T4& rgb8) {
     const std::string e = "vae.encoder";
     T4 x = b.alloc(rgb8.N, rgb8.H, rgb8.W, 128);
-    b.direct(e + ".conv_in", rgb8, 3, direct_w(e + ".conv_in", 3), x, 0, nullptr, 0);
+    small_cin_conv(b, e + ".conv_in", rgb8, 3, x);
     const int ch[5] = {128, 128, 256, 512, 512};
     for (int i = 0; i < 4; ++i) {
       for (int j = 0; j < 2; ++j) {
@@ -542,7 +559,7 @@ struct gp_engine {
     compute_temb();
     const std::string u = "unet";
     T4 x = b.alloc(lat8.N, lat8.H, lat8.W, 320);
-    b.direct(u + ".conv_in", lat8, 4, direct_w(u + ".conv_in", 4), x, 0, nullptr, 0);
+    small_cin_conv(b, u + ".conv_in", lat8, 4, x);
     std::vector<T4> skips = {x};
     int cin = 320;
     for (int i = 0; i < 4; ++i) {
@@ -653,7 +670,7 @@ struct gp_engine {
   void vae_decoder(Builder& b, const T4& z8, float* out_f32) {
     const std::string d = "vae.decoder";
     T4 x = b.alloc(z8.N, z8.H, z8.W, 512);
-    b.direct(d + ".conv_in", z8, 4, direct_w(d + ".conv_in", 4), x, 0, nullptr, 0);
+    small_cin_conv(b, d + ".conv_in", z8, 4, x);
     x = vae_mid(b, d + ".mid_block", x);
     const int oc[4] = {512, 512, 256, 128};
     for (int i = 0; i < 4; ++i) {

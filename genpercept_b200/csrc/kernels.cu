@@ -102,7 +102,21 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
   const uint16_t* base = x + ((long long)n * HW) * C + threadIdx.x * 8;
-  for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+  const int step = blockDim.y;
+  long long p = p0 + threadIdx.y;
+  for (; p + 3 * step < p1; p += 4 * step) {      // four independent 16-byte loads in flight
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + (long long)k * step) * C));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8<BF16>(u[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
+    }
+  }
+  for (; p < p1; p += step) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * C));
     float f[8];
     unpack8<BF16>(u, f);
@@ -142,25 +156,51 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* 
 
 template <bool BF16, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, int C, const float* __restrict__ ss,
-                                int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, long long total_vec) {
-  const int nvec = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const long long pix = i / nvec;           // n*HW + p
-    const int n = (int)(pix / HW);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * C + v * 8));
-    float f[8];
-    unpack8<BF16>(u, f);
-    const float4* sp = reinterpret_cast<const float4*>(ss + ((long long)n * Ctot + coff + v * 8) * 2);
+                                int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, int pix_per_block) {
+  // blockDim = (C/8 channel vectors, PIX pixel lanes); grid = (pixel chunks, N).  The thread's 8
+  // (scale, shift) pairs live in registers for its whole pixel strip.
+  const int n = blockIdx.y;
+  float sc[8], sh[8];
+  {
+    const float4* sp = reinterpret_cast<const float4*>(ss + ((long long)n * Ctot + coff + threadIdx.x * 8) * 2);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float4 a = __ldg(sp + e);       // (scale, shift) x 2 channels
-      float y0 = f[2 * e] * a.x + a.y, y1 = f[2 * e + 1] * a.z + a.w;
-      if (SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      f[2 * e] = y0; f[2 * e + 1] = y1;
+      const float4 a = __ldg(sp + e);
+      sc[2 * e] = a.x; sh[2 * e] = a.y; sc[2 * e + 1] = a.z; sh[2 * e + 1] = a.w;
     }
-    *reinterpret_cast<uint4*>(y + pix * y_cstride + coff + v * 8) = pack8<BF16>(f);
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > HW) p1 = HW;
+  const uint16_t* xb = x + ((long long)n * HW) * C + threadIdx.x * 8;
+  uint16_t* yb = y + ((long long)n * HW) * y_cstride + coff + threadIdx.x * 8;
+  const int step = blockDim.y;
+  long long p = p0 + threadIdx.y;
+  for (; p + 3 * step < p1; p += 4 * step) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (p + (long long)k * step) * C));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8<BF16>(u[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = f[e] * sc[e] + sh[e];
+        f[e] = SILU ? silu_f(v) : v;
+      }
+      *reinterpret_cast<uint4*>(yb + (p + (long long)k * step) * y_cstride) = pack8<BF16>(f);
+    }
+  }
+  for (; p < p1; p += step) {
+    float f[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(xb + p * C)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = f[e] * sc[e] + sh[e];
+      f[e] = SILU ? silu_f(v) : v;
+    }
+    *reinterpret_cast<uint4*>(yb + p * y_cstride) = pack8<BF16>(f);
   }
 }
 
@@ -502,14 +542,19 @@ cudaError_t gn_finalize(const float* sums, const float* gamma, const float* beta
 
 cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* ss, int Ctot, int coff, void* y,
                      int y_cstride, bool silu, bool bf16, cudaStream_t s) {
-  const long long total_vec = (long long)N * HW * (C / 8);
-  const int blocks = blocks_for(total_vec, 256);
+  const int nvec = C / 8;
+  int pix = 256 / nvec;
+  if (pix < 1) pix = 1;
+  if (pix > 32) pix = 32;
+  const int pix_per_block = pix * 16;
+  dim3 block(nvec, pix);
+  dim3 grid((unsigned)((HW + pix_per_block - 1) / pix_per_block), N);
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   if (silu)
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<blocks, 256, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, total_vec)));
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block)));
   else
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<blocks, 256, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, total_vec)));
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block)));
   return cudaGetLastError();
 }
 

@@ -31,9 +31,7 @@ def sharded_infer(infer_fn, rgb, stacked=True, group=None):
     if not stacked:
         return local
     sizes = [shard_bounds(B, ws, r)[1] - shard_bounds(B, ws, r)[0] for r in range(ws)]
-    if local is None:   # more ranks than images: learn the map shape from rank 0
-        shape = [torch.zeros(3, dtype=torch.int64, device=rgb.device if rgb.is_cuda else "cpu")]
-    ref = local
+    ref = local          # None when there are more ranks than images: shape comes from the others
     meta = torch.tensor(list(ref.shape[1:]) if ref is not None else [0, 0, 0], dtype=torch.int64,
                         device=ref.device if ref is not None else ("cuda" if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"))
     dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=group)
