@@ -97,11 +97,12 @@ static int choose_bn(int cout, int force) {
   const int n = ceil_div(cout, 256);
   return ceil_div(ceil_div(cout, n), 16) * 16;
 }
-// pick the TW x TH = 128 patch with the least padding waste (ties: wider rows)
-static void choose_tile(int gw, int gh, int* tw, int* th, int* shift) {
+// pick the TW x TH = `rows` (128 or 256) patch with the least padding waste (ties: wider rows)
+static void choose_tile(int gw, int gh, int rows, int* tw, int* th, int* shift) {
   double best = 1e30;
   for (int s = 7; s >= 0; --s) {
-    const int w = 1 << s, h = 128 >> s;
+    const int w = 1 << s, h = rows >> s;
+    if (h > 256) continue;
     const double waste = (double)ceil_div(gw, w) * w * ceil_div(gh, h) * h / ((double)gw * gh);
     if (waste < best - 1e-9) { best = waste; *tw = w; *th = h; *shift = s; }
   }
@@ -153,12 +154,13 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     const long long ntok = (long long)N * H * W;
     GP_REQUIRE(ntok < (1LL << 31), name + ": too many tokens");
     p.gridW = (int)ntok; p.gridH = 1;
-    p.TW = 128; p.TH = 1; p.tw_shift = 7;
+    p.MT = (p.BN <= 128 && ntok >= 256 * 148) ? 2 : 1;
+    p.TW = 128 * p.MT; p.TH = 1; p.tw_shift = p.MT == 2 ? 8 : 7;
     p.nseg[0] = 1;
     p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(s0.C, 64)};
     p.outW = (int)ntok; p.outH = 1;
     p.out_pix_stride = out_c; p.out_row_stride = 0;
-    check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.C, ntok * s0.C, ntok * s0.C, 128, 1, bf16_),
+    check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.C, ntok * s0.C, ntok * s0.C, p.TW, 1, bf16_),
                name + ": tmap A");
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   } else {
@@ -170,7 +172,9 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     p.out_z1 = (long long)Ho * Wo * out_c;
     p.gridW = (a.mode == 3) ? W : Wo;
     p.gridH = (a.mode == 3) ? H : Ho;
-    choose_tile(p.gridW, p.gridH, &p.TW, &p.TH, &p.tw_shift);
+    // two accumulator tiles per CTA when the N tile is narrow and there is enough work to fill the GPU
+    p.MT = (p.BN <= 128 && (long long)p.gridW * p.gridH * N * (a.mode == 3 ? 4 : 1) >= 256LL * 148) ? 2 : 1;
+    choose_tile(p.gridW, p.gridH, 128 * p.MT, &p.TW, &p.TH, &p.tw_shift);
     int nmap = 0;
     if (a.mode == 0 || a.mode == 3) {
       GP_REQUIRE(a.srcs.size() + a.sc.size() <= 4, name + ": too many sources");
@@ -377,40 +381,43 @@ void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const Nor
   int ctot = 0;
   for (auto& s : srcs) ctot += s.C;
   GP_REQUIRE(ctot == out.C && nw.C == ctot && ctot % groups == 0, name + ": GroupNorm channel mismatch");
-  if (measuring_) return;
   const int N = out.N;
   const long long HW = (long long)out.H * out.W;
-  float* sums = gn_sums;
-  float* ss = gn_ss;
-  const bool bf = bf16_;
-  std::vector<const void*> xs;
-  std::vector<int> cs;
-  for (auto& s : srcs) { xs.push_back(ptr(s)); cs.push_back(s.C); }
-  void* y = ptr(out);
-  const float* gamma = nw.gamma;
-  const float* beta = nw.beta;
-  double bytes = 0;
-  for (auto& s : srcs) bytes += 2.0 * s.bytes();
-  bytes += (double)out.bytes();
-  push(name, 2 + 2 * (int)srcs.size(), 0, bytes, [=](cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * ctot * 2 * sizeof(float), s);
-    if (e != cudaSuccess) return e;
-    int coff = 0;
-    for (size_t i = 0; i < xs.size(); ++i) {
-      e = gn_stats(xs[i], N, HW, cs[i], sums, ctot, coff, bf, s);
+  const int chunks = gn_chunks(N, HW);
+  const size_t part_off = arena_.alloc((size_t)N * chunks * ctot * 2 * sizeof(float));
+  if (!measuring_) {
+    float* partial = reinterpret_cast<float*>(raw_ptr(part_off));
+    float* ss = gn_ss;
+    const bool bf = bf16_;
+    std::vector<const void*> xs;
+    std::vector<int> cs;
+    for (auto& s : srcs) { xs.push_back(ptr(s)); cs.push_back(s.C); }
+    void* y = ptr(out);
+    const float* gamma = nw.gamma;
+    const float* beta = nw.beta;
+    double bytes = 0;
+    for (auto& s : srcs) bytes += 2.0 * s.bytes();
+    bytes += (double)out.bytes();
+    push(name, 1 + 2 * (int)srcs.size(), 0, bytes, [=](cudaStream_t s) {
+      cudaError_t e;
+      int coff = 0;
+      for (size_t i = 0; i < xs.size(); ++i) {
+        e = gn_stats(xs[i], N, HW, cs[i], partial, chunks, ctot, coff, bf, s);
+        if (e != cudaSuccess) return e;
+        coff += cs[i];
+      }
+      e = gn_finalize(partial, chunks, gamma, beta, N, ctot, groups, HW, eps, ss, s);
       if (e != cudaSuccess) return e;
-      coff += cs[i];
-    }
-    e = gn_finalize(sums, gamma, beta, N, ctot, groups, HW, eps, ss, s);
-    if (e != cudaSuccess) return e;
-    coff = 0;
-    for (size_t i = 0; i < xs.size(); ++i) {
-      e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s);
-      if (e != cudaSuccess) return e;
-      coff += cs[i];
-    }
-    return cudaSuccess;
-  });
+      coff = 0;
+      for (size_t i = 0; i < xs.size(); ++i) {
+        e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s);
+        if (e != cudaSuccess) return e;
+        coff += cs[i];
+      }
+      return cudaSuccess;
+    });
+  }
+  arena_.release(part_off);
 }
 
 void Builder::ln(const std::string& name, const T4& x, const NormW& nw, float eps, const T4& out) {

@@ -1229,9 +1229,17 @@ gp_status gp_groupnorm(int dtype, const void* x, int N, int H, int W, int C, int
     nw.C = C;
     nw.gamma = te.e.upload(std::vector<float>(gamma_host, gamma_host + C));
     nw.beta = te.e.upload(std::vector<float>(beta_host, beta_host + C));
-    Builder b(te.e.bf16, false, nullptr);
-    b.gn_sums = te.e.upload(std::vector<float>((size_t)N * C * 2, 0.f));
-    b.gn_ss = te.e.upload(std::vector<float>((size_t)N * C * 2, 0.f));
+    float* ss = te.e.upload(std::vector<float>((size_t)N * C * 2, 0.f));
+    void* arena = nullptr;
+    {
+      Builder m(te.e.bf16, true, nullptr);
+      m.gn("gp_groupnorm", {m.external(x, N, H, W, C)}, nw, groups, eps, silu != 0, m.external(y, N, H, W, C));
+      GP_CUDA(cudaMalloc(&arena, m.arena_bytes() + 1024));
+      te.e.dev_allocs.push_back(arena);
+    }
+    // external tensors are addressed relative to the scratch arena's base
+    Builder b(te.e.bf16, false, reinterpret_cast<uint8_t*>(arena));
+    b.gn_ss = ss;
     b.gn("gp_groupnorm", {b.external(x, N, H, W, C)}, nw, groups, eps, silu != 0, b.external(y, N, H, W, C));
     run_all(b, s);
     GP_CUDA(cudaStreamSynchronize(s));

@@ -158,21 +158,30 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t ts = tmem_base + lane_off + (j & 1) * 128;
       const int kvalid = min(128, T - j * 128);
-      // pass 1: row maximum
-      float mx = m;
-#pragma unroll 1
+      // pass 1: row maximum.  One warp per SM sub-partition runs this, so ALU latency is only hidden
+      // by instruction-level parallelism: 4 independent max chains, TMEM loads one chunk ahead.
+      uint32_t ra[32], rb[32];
+      float mx0 = m, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      tmem_ld_32x32(ts, ra);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + c * 32, r);
         tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? rb : ra;
+        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
         if (kvalid == 128) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(r[q]));
+          for (int q = 0; q < 32; q += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
+            mx1 = fmaxf(mx1, __uint_as_float(cur[q + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(cur[q + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(cur[q + 3]));
+          }
         } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) if (c * 32 + q < kvalid) mx = fmaxf(mx, __uint_as_float(r[q]));
+          for (int q = 0; q < 32; ++q) if (c * 32 + q < kvalid) mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
         }
       }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float alpha = ex2((m - mx) * c2);
       if (j > 0) {
         mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1, 16);
@@ -188,21 +197,25 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         }
       }
       l *= alpha;
-      // pass 2: probabilities -> shared memory (A operand of P.V), row sum
+      // pass 2: probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
       const float mb = mx * c2;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      tmem_ld_32x32(ts, ra);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float e = ex2(__uint_as_float(r[q]) * c2 - mb);
-          if (kvalid != 128 && c * 32 + q >= kvalid) e = 0.f;
-          pv[q] = e;
-          l += e;
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? rb : ra;
+        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
+        float pv[32];
+        if (kvalid == 128) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) pv[q] = ex2(__uint_as_float(cur[q]) * c2 - mb);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) pv[q] = (c * 32 + q < kvalid) ? ex2(__uint_as_float(cur[q]) * c2 - mb) : 0.f;
         }
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) { l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3]; }
         uint8_t* dst = prow + (c >> 1) * 16384;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -214,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
           *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + i) ^ sw) << 4)) = u;
         }
       }
+      l += (l0 + l1) + (l2 + l3);
       tc_fence_before();
       mbar_arrive(&s_empty[j & 1]);
       fence_proxy_async_smem();

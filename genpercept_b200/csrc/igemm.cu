@@ -1,10 +1,15 @@
 // tcgen05 implicit-GEMM kernel (see igemm.h for the operand model).
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over a static round-robin tile list):
-//   warp 0 lane 0 : TMA producer  (A box + B box per 64-channel K block, `stages`-deep ring)
-//   warp 1 lane 0 : MMA issuer    (4 x tcgen05.mma 128xBNx16 per K block; commit frees the slot)
-//   warp 2        : TMEM allocator (512 columns = 2 accumulator buffers of up to 256 columns)
+//   warp 0 lane 0 : TMA producer A (activation box per 64-channel K block, `stages`-deep ring)
+//   warp 3 lane 0 : TMA producer B (weight box per K block) — its own thread: one thread issuing
+//                   both boxes plus the barrier traffic could not keep up with BN=128 tiles
+//                   (ncu r1a: tensor pipe 45 % active on the 128->128 convs, DRAM/L2 not saturated)
+//   warp 1 lane 0 : MMA issuer    (MT x 4 tcgen05.mma 128xBNx16 per K block; commit frees the slot)
+//   warp 2        : TMEM allocator (512 columns = 2 accumulator buffers x MT tiles)
 //   warps 4..7    : epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/residual/act -> HBM)
+// MT = 2 (a 256-pixel M tile per CTA, two accumulators sharing every weight box) when BN <= 128:
+// halves the weight traffic and the per-byte barrier / TMA issue cost of the narrow-N layers.
 #include "igemm.h"
 
 #include <cuda_bf16.h>
@@ -19,7 +24,7 @@ namespace gp {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kABytes = kBM * kBK * 2;       // 16 KiB
+constexpr int kABytes = kBM * kBK * 2;       // 16 KiB per 128-row tile
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns between the two accumulator buffers
 constexpr int kMaxSmem = 227 * 1024;
@@ -59,12 +64,22 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
   }
 }
+template <bool BF16>
+__device__ __forceinline__ void add8(float* v, const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] += cvt16<BF16>((uint16_t)(w[e] & 0xFFFF));
+    v[2 * e + 1] += cvt16<BF16>((uint16_t)(w[e] >> 16));
+  }
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = kABytes + p.BN * 128;
+  const int a_bytes = kABytes * p.MT;
+  const int stage_bytes = a_bytes + p.BN * 128;
   const int stages = p.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], 2);    // producer A + producer B
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer A
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -103,28 +118,43 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int cls = p.cls_from_z0 ? t.z0 : 0;
       const int a_n = t.z1 * p.a_n_z1 + t.z0 * p.a_n_z0;
       const int a_k0 = t.z0 * p.a_k_z0;
-      const int b_z = t.z1 * p.b_z_z1 + t.z0 * p.b_z_z0;
-      const int b_row = t.z0 * p.b_row_z0 + t.n_tile * p.BN;
-      const int b_k0 = t.z0 * p.b_k_z0;
       const int x0 = t.tx * p.TW, y0 = t.ty * p.TH;
-      int kb = 0;
       const int ns = p.nseg[cls];
       for (int s = 0; s < ns; ++s) {
         const IgemmSeg sg = p.seg[cls][s];
-        for (int c = 0; c < sg.nchunks; ++c, ++kb) {
+        const CUtensorMap* tm = &p.tmA[sg.map];
+        const int xs = x0 + sg.dx, ys = y0 + sg.dy;
+        for (int c = 0; c < sg.nchunks; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          uint8_t* sA = smem + stage * stage_bytes;
-          uint8_t* sB = sA + kABytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_4d(sA, &p.tmA[sg.map], &full_bar[stage], a_k0 + c * kBK, x0 + sg.dx, y0 + sg.dy, a_n);
-          tma_load_3d(sB, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
+          tma_load_4d(smem + stage * stage_bytes, tm, &full_bar[stage], a_k0 + c * kBK, xs, ys, a_n);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================================================================== TMA producer B
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t b_bytes = (uint32_t)p.BN * 128;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int cls = p.cls_from_z0 ? t.z0 : 0;
+      const int b_z = t.z1 * p.b_z_z1 + t.z0 * p.b_z_z0;
+      const int b_row = t.z0 * p.b_row_z0 + t.n_tile * p.BN;
+      const int b_k0 = t.z0 * p.b_k_z0;
+      const int nkb = p.nkb[cls];
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 5);
+        mbar_expect_tx(&full_bar[stage], b_bytes);
+        tma_load_3d(smem + stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================================================================== MMA issuer
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
+    const int mt = p.MT;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -140,12 +170,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_bytes);
+        for (int h = 0; h < mt; ++h) {
+          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + h * kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
-          umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
+            umma_f16(d_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -157,8 +189,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int wq = warp - 4;                 // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
-    const int row = wq * 32 + lane;
-    const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool f32out = (p.flags & IG_OUT_F32_NCHW) != 0;
@@ -167,116 +197,121 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int cls = p.cls_from_z0 ? t.z0 : 0;
-      const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
-      const bool valid = gy < p.gridH && gx < p.gridW;
-      const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
-      const long long pix_off = t.z1 * p.out_z1 + t.z0 * p.out_z0 + (long long)oy * p.out_row_stride +
-                                (long long)ox * p.out_pix_stride;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride;
       const int n_base = t.n_tile * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t r[32];
-        const int ncols = (p.BN - c0 >= 32) ? 32 : 16;
-        if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
-        tmem_ld_wait();
-        const int n0 = n_base + c0;
-        if (!valid || n0 >= p.Cout) continue;
-        float v[32];
+      bool waited = false;
+      for (int h = 0; h < p.MT; ++h) {
+        const int row = h * 128 + wq * 32 + lane;
+        const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
+        const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
+        const bool valid = gy < p.gridH && gx < p.gridW;
+        const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
+        const long long pix_off = t.z1 * p.out_z1 + t.z0 * p.out_z0 + (long long)oy * p.out_row_stride +
+                                  (long long)ox * p.out_pix_stride;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          const int ncols = (p.BN - c0 >= 32) ? 32 : 16;
+          const int n0 = n_base + c0;
+          const int nvalid = min(ncols, p.Cout - n0);
+          const bool live = valid && nvalid > 0;
+          const long long off = pix_off + n0;
+          const bool vec = !f32out && live && (nvalid == ncols) && ((off & 7) == 0);
+          // operands that do not depend on the accumulator are fetched BEFORE waiting on it
+          float bz[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-        const int nvalid = min(ncols, p.Cout - n0);
-        if (p.bias != nullptr) {
-          if (nvalid == 32) {
+          for (int q = 0; q < 32; ++q) bz[q] = 0.f;
+          if (live && p.bias != nullptr) {
+            if (nvalid == 32) {
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q));
-              v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
+              for (int q = 0; q < 32; q += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q));
+                bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) if (q < nvalid) bz[q] = __ldg(p.bias + n0 + q);
             }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += __ldg(p.bias + n0 + q);
           }
-        }
-        if (f32out) {
-          float* o = reinterpret_cast<float*>(p.out);
+          uint4 r1[4], r2[4];
+          const bool has1 = vec && p.res1 != nullptr, has2 = vec && p.res2 != nullptr;
+          if (has1) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            if (q < nvalid) {
-              float x = v[q];
-              if (relu) x = fmaxf(x, 0.f);
-              if (aff) x = fminf(fmaxf((x + 1.f) * 0.5f, 0.f), 1.f);
-              o[(((long long)t.z1 * p.Cout + (n0 + q)) * p.outH + oy) * p.outW + ox] = x;
+            for (int q = 0; q < 4; ++q) if (q * 8 < ncols) r1[q] = rp[q];
+          }
+          if (has2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q * 8 < ncols) r2[q] = rp[q];
+          }
+          if (!waited) {
+            mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t r[32];
+          if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (!live) continue;
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
+          if (f32out) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              if (q < nvalid) {
+                float x = v[q];
+                if (relu) x = fmaxf(x, 0.f);
+                if (aff) x = fminf(fmaxf((x + 1.f) * 0.5f, 0.f), 1.f);
+                o[(((long long)t.z1 * p.Cout + (n0 + q)) * p.outH + oy) * p.outW + ox] = x;
+              }
             }
+            continue;
           }
-          continue;
-        }
-        const long long off = pix_off + n0;
-        const bool vec = (nvalid == ncols) && ((off & 7) == 0);
-        if (p.res1 != nullptr) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res1) + off;
+          if (has1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r1[q]);
+          } else if (p.res1 != nullptr) {
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res1) + off;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
+          }
+          if (has2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r2[q]);
+          } else if (p.res2 != nullptr) {
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res2) + off;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
+          }
+          if (relu) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
           if (vec) {
 #pragma unroll
             for (int q = 0; q < 32; q += 8) {
               if (q < ncols) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + q);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[q + 2 * e] += cvt16<BF16>((uint16_t)(w[e] & 0xFFFF));
-                  v[q + 2 * e + 1] += cvt16<BF16>((uint16_t)(w[e] >> 16));
-                }
+                uint4 u;
+                u.x = pack16<BF16>(v[q], v[q + 1]);
+                u.y = pack16<BF16>(v[q + 2], v[q + 3]);
+                u.z = pack16<BF16>(v[q + 4], v[q + 5]);
+                u.w = pack16<BF16>(v[q + 6], v[q + 7]);
+                *reinterpret_cast<uint4*>(op + q) = u;
               }
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
-          }
-        }
-        if (p.res2 != nullptr) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res2) + off;
-          if (vec) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 8) {
-              if (q < ncols) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + q);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[q + 2 * e] += cvt16<BF16>((uint16_t)(w[e] & 0xFFFF));
-                  v[q + 2 * e + 1] += cvt16<BF16>((uint16_t)(w[e] >> 16));
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
-          }
-        }
-        if (relu) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
-        }
-        uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
-        if (vec) {
-#pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            if (q < ncols) {
-              uint4 u;
-              u.x = pack16<BF16>(v[q], v[q + 1]);
-              u.y = pack16<BF16>(v[q + 2], v[q + 3]);
-              u.z = pack16<BF16>(v[q + 4], v[q + 5]);
-              u.w = pack16<BF16>(v[q + 6], v[q + 7]);
-              *reinterpret_cast<uint4*>(op + q) = u;
+            for (int q = 0; q < 32; ++q) {
+              if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
             }
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
-          }
         }
+      }
+      if (!waited) {   // unreachable (BN >= 16), kept so the barrier protocol can never desynchronise
+        mbar_wait(&tfull_bar[acc], acc_phase, 4);
+        tc_fence_after();
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -345,11 +380,15 @@ cudaError_t make_tmap_b(CUtensorMap* m, const void* base, long long K, long long
 }
 
 size_t igemm_smem_bytes(const IgemmParams& p) {
-  return (size_t)p.stages * (kABytes + p.BN * 128) + (2 * p.stages + 4) * 8 + 16 + 1024;
+  return (size_t)p.stages * (kABytes * p.MT + p.BN * 128) + (2 * p.stages + 4) * 8 + 16 + 1024;
 }
 
 const char* igemm_finalize(IgemmParams* p) {
-  if (p->TW * p->TH != kBM) return "TW*TH must be 128";
+  if (p->MT == 0) p->MT = 1;
+  if (p->MT != 1 && p->MT != 2) return "MT must be 1 or 2";
+  if (p->MT == 2 && p->BN > 128) return "MT=2 needs BN <= 128 (TMEM: 2 buffers x 2 tiles x BN columns)";
+  if (p->TW * p->TH != kBM * p->MT) return "TW*TH must be 128*MT";
+  if (p->TW > 256 || p->TH > 256) return "TMA box dims are limited to 256";
   if ((1 << p->tw_shift) != p->TW) return "TW must be a power of two";
   if (p->BN < 16 || p->BN > 256 || (p->BN % 16)) return "BN must be a multiple of 16 in [16,256]";
   if (p->Z0 < 1 || p->Z1 < 1) return "bad batch dims";
@@ -368,7 +407,7 @@ const char* igemm_finalize(IgemmParams* p) {
   long long total = (long long)p->n_tiles_n * p->tiles_x * p->tiles_y * p->Z0 * p->Z1;
   if (total > 0x7fffffffLL) return "too many tiles";
   p->total_tiles = (int)total;
-  const int stage_bytes = kABytes + p->BN * 128;
+  const int stage_bytes = kABytes * p->MT + p->BN * 128;
   int st = (kMaxSmem - 2048) / stage_bytes;
   if (st > 8) st = 8;
   if (st < 2) return "tile too large for shared memory";

@@ -43,7 +43,8 @@ struct IgemmParams {
   int nkb[kMaxClasses];          // total K blocks per class
   int8_t cls_py[kMaxClasses], cls_px[kMaxClasses];
   int out_sy, out_sx;            // output pixel = tile-grid pixel * s + (py, px)
-  int TW, TH, tw_shift;          // M tile = TH rows x TW cols, TW*TH == 128, TW = 1 << tw_shift
+  int MT;                        // 128-row accumulator tiles per CTA tile: 1, or 2 when BN <= 128
+  int TW, TH, tw_shift;          // M tile = TH rows x TW cols, TW*TH == 128*MT, TW = 1 << tw_shift
   int tiles_x, tiles_y, n_tiles_n, BN;
   int gridW, gridH;              // valid extent of the tile grid (pixels)
   int Z1, Z0;                    // batch dims (z1 outer: image; z0 inner: parity class / head)

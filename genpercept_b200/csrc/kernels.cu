@@ -86,15 +86,16 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
 }
 
 // ------------------------------------------------------------------------------ GroupNorm
+// Deterministic two-level reduction (no atomics, fixed summation order => bit-reproducible runs):
+//   gn_stats   : block (C/8 vectors x PIX pixel lanes) reduces its pixel chunk -> partial[n][chunk][c][2]
+//   gn_finalize: one warp per (n, group) sums the partials in a fixed order -> scale/shift per channel
 template <bool BF16>
-__global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, int C, float* sums, int Ctot,
-                                int coff, int pix_per_block) {
-  extern __shared__ float sh[];   // [C][2]
+__global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, int C, float* __restrict__ partial,
+                                int Ctot, int coff, int pix_per_block) {
+  extern __shared__ float sh[];   // [PIX][C][2]
   const int n = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < 2 * C; i += nthr) sh[i] = 0.f;
-  __syncthreads();
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > HW) p1 = HW;
@@ -123,35 +124,43 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
   }
+  float* mine = sh + ((size_t)threadIdx.y * C + threadIdx.x * 8) * 2;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    atomicAdd(&sh[(threadIdx.x * 8 + e) * 2], s[e]);
-    atomicAdd(&sh[(threadIdx.x * 8 + e) * 2 + 1], q[e]);
-  }
+  for (int e = 0; e < 8; ++e) { mine[2 * e] = s[e]; mine[2 * e + 1] = q[e]; }
   __syncthreads();
-  float* dst = sums + ((long long)n * Ctot + coff) * 2;
-  for (int i = tid; i < 2 * C; i += nthr) atomicAdd(&dst[i], sh[i]);
+  float* dst = partial + (((long long)n * gridDim.x + blockIdx.x) * Ctot + coff) * 2;
+  for (int i = tid; i < 2 * C; i += nthr) {
+    float a = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y) a += sh[(size_t)y * C * 2 + i];
+    dst[i] = a;
+  }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int N, int Ctot, int groups, float inv_count,
                                    float eps, float* __restrict__ ss) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * Ctot) return;
-  const int n = idx / Ctot, c = idx % Ctot;
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (n, group)
+  if (wid >= N * groups) return;
+  const int n = wid / groups, g = wid % groups;
   const int cpg = Ctot / groups;
-  const int g0 = (c / cpg) * cpg;
+  const int entries = cpg * chunks;
   float s = 0.f, q = 0.f;
-  for (int i = 0; i < cpg; ++i) {
-    s += sums[((long long)n * Ctot + g0 + i) * 2];
-    q += sums[((long long)n * Ctot + g0 + i) * 2 + 1];
+  for (int i = lane; i < entries; i += 32) {
+    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
+    const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * chunks + ch) * Ctot + c) * 2);
+    s += v.x; q += v.y;
   }
+  s = warp_sum(s); q = warp_sum(q);
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
-  const float sc = rstd * gamma[c];
-  ss[(long long)idx * 2] = sc;
-  ss[(long long)idx * 2 + 1] = beta[c] - mean * sc;
+  for (int i = lane; i < cpg; i += 32) {
+    const int c = g * cpg + i;
+    const float sc = rstd * gamma[c];
+    ss[((long long)n * Ctot + c) * 2] = sc;
+    ss[((long long)n * Ctot + c) * 2 + 1] = beta[c] - mean * sc;
+  }
 }
 
 template <bool BF16, bool SILU>
@@ -517,26 +526,34 @@ cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* sums, int Ctot, int coff, bool bf16,
-                     cudaStream_t s) {
+int gn_chunks(int N, long long HW) {
+  (void)N;   // independent of the batch size: a batch of B equals B batches of 1 bit for bit
+  long long c = (HW + 63) / 64;
+  if (c > 256) c = 256;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, int chunks, int Ctot, int coff,
+                     bool bf16, cudaStream_t s) {
   const int nvec = C / 8;
   int pix = 256 / nvec;
   if (pix < 1) pix = 1;
   if (pix > 32) pix = 32;
-  const int pix_per_block = pix * 64;
+  const int pix_per_block = (int)((HW + chunks - 1) / chunks);
   dim3 block(nvec, pix);
-  dim3 grid((unsigned)((HW + pix_per_block - 1) / pix_per_block), N);
-  const size_t smem = (size_t)2 * C * sizeof(float);
+  dim3 grid((unsigned)chunks, N);
+  const size_t smem = (size_t)pix * C * 2 * sizeof(float);
   GP_DISPATCH_BF16(bf16, (gn_stats_kernel<BF><<<grid, block, smem, s>>>(reinterpret_cast<const uint16_t*>(x), HW, C,
-                                                                         sums, Ctot, coff, pix_per_block)));
+                                                                         partial, Ctot, coff, pix_per_block)));
   return cudaGetLastError();
 }
 
-cudaError_t gn_finalize(const float* sums, const float* gamma, const float* beta, int N, int Ctot, int groups,
-                        long long HW, float eps, float* ss, cudaStream_t s) {
-  const int total = N * Ctot;
+cudaError_t gn_finalize(const float* partial, int chunks, const float* gamma, const float* beta, int N, int Ctot,
+                        int groups, long long HW, float eps, float* ss, cudaStream_t s) {
+  const int warps = N * groups;
   const float inv_count = 1.0f / ((float)HW * (float)(Ctot / groups));
-  gn_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(sums, gamma, beta, N, Ctot, groups, inv_count, eps, ss);
+  gn_finalize_kernel<<<(warps + 7) / 8, 256, 0, s>>>(partial, chunks, gamma, beta, N, Ctot, groups, inv_count, eps, ss);
   return cudaGetLastError();
 }
 

@@ -28,12 +28,13 @@ struct DirectConvParams {
 };
 cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s);
 
-// GroupNorm: per-(n, channel) sum / sum-of-squares -> per-(n, channel) scale / shift -> apply.
-cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* sums /*[N][Ctot][2]*/, int Ctot,
-                     int coff, bool bf16, cudaStream_t s);
-cudaError_t gn_finalize(const float* sums, const float* gamma, const float* beta, int N, int Ctot,
-                        int groups, long long HW, float eps, float* scale_shift /*[N][Ctot][2]*/,
-                        cudaStream_t s);
+// GroupNorm, deterministic: per-chunk partial sums [N][chunks][Ctot][2] -> per-(n, channel)
+// scale / shift -> apply.  chunks = gn_chunks(N, HW) for every source of one normalisation.
+int gn_chunks(int N, long long HW);
+cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, int chunks, int Ctot, int coff,
+                     bool bf16, cudaStream_t s);
+cudaError_t gn_finalize(const float* partial, int chunks, const float* gamma, const float* beta, int N, int Ctot,
+                        int groups, long long HW, float eps, float* scale_shift /*[N][Ctot][2]*/, cudaStream_t s);
 cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* scale_shift, int Ctot,
                      int coff, void* y, int y_cstride, bool silu, bool bf16, cudaStream_t s);
 

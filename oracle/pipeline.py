@@ -14,8 +14,11 @@ ONE_CHANNEL_MODES = ("depth", "matting", "dis", "disparity")   # genpercept_pipe
 
 
 class OraclePipeline:
-    def __init__(self, state, text_embed, use_dpt=False):
-        """state: {"unet": sd, "vae": sd, "dpt": sd or None} with diffusers keys (fp32 tensors)."""
+    def __init__(self, state, text_embed, use_dpt=False, dtype=torch.float32):
+        """state: {"unet": sd, "vae": sd, "dpt": sd or None} with diffusers keys (fp32 tensors).
+        dtype=torch.float16 emulates the reference's ``--half_precision`` run (run.py:273-281:
+        every module and activation in fp16) and is only used to calibrate test tolerances."""
+        self.dtype = dtype
         self.unet = UNet2DConditionModel().eval()
         self.vae = AutoencoderKL().eval()
         sd_unet = dict(state["unet"])
@@ -29,8 +32,13 @@ class OraclePipeline:
         if use_dpt:
             self.head = DPTNeckHeadIdentity().eval()
             self.head.load_state_dict(state["dpt"], strict=True)
-        self.text_embed = text_embed.float().reshape(1, -1, 1024)
+        self.text_embed = text_embed.float().reshape(1, -1, 1024).to(dtype)
         self.scheduler = DDIMOneStep()
+        if dtype != torch.float32:
+            self.unet.to(dtype)
+            self.vae.to(dtype)
+            if self.head is not None:
+                self.head.to(dtype)
 
     @torch.no_grad()
     def encode_rgb(self, rgb_in):                       # :488-505
@@ -58,7 +66,7 @@ class OraclePipeline:
         timesteps = self.scheduler.set_timesteps(1)
         if fix_timesteps:
             timesteps = torch.tensor([fix_timesteps]).long()
-        rgb_latent = self.encode_rgb(rgb_in.float())
+        rgb_latent = self.encode_rgb(rgb_in.to(self.dtype))
         pred_latent = rgb_latent
         inter = {"rgb_latent": rgb_latent}
         if self.head is None:

@@ -111,7 +111,8 @@ class UNet2DConditionModel(nn.Module):
 
     def time_embed(self, timestep, batch):
         t = torch.as_tensor(timestep).reshape(-1).expand(batch)
-        return self.time_embedding(self.time_proj(t))
+        # custom_unet.py:168: the fp32 sinusoid is cast to the sample dtype before the MLP
+        return self.time_embedding(self.time_proj(t).to(self.conv_in.weight.dtype))
 
     def forward(self, sample, timestep, encoder_hidden_states, return_feature=False):
         b = sample.shape[0]

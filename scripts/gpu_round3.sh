@@ -7,3 +7,4 @@ echo "bench exit $?"; tail -n 3 gpurun_out/bench.log | cut -c1-1500; tail -n 5 g
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fattn_kernel -c 2 -f -o gpurun_out/prof_fattn \
   python scripts/prof_attn.py > gpurun_out/prof_attn.log 2>&1
 echo "ncu fattn exit $?"; tail -n 4 gpurun_out/prof_attn.log
+timeout 300 python scripts/bench_convs.py > gpurun_out/bench_convs.log 2>&1; tail -n 14 gpurun_out/bench_convs.log
