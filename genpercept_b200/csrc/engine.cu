@@ -81,6 +81,7 @@ struct Plan {
   float* out_f32 = nullptr;         // [B,3,H,W]
   std::map<int, cudaGraphExec_t> graphs;   // by out_channels
   double igemm_flops = 0;
+  int eager_runs = 0;                       // the first pass runs eagerly (kernel attributes, lazy init), then graphs
   int64_t launches = 0;
 };
 
@@ -977,7 +978,7 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
     else throw GpError(GP_ERR_INVALID, "gp_infer: rgb dtype must be u8, f16 or f32");
     GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, npix * 3 * esz, rgb_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     GP_CUDA(preprocess_rgb(p->in_staging, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s));
-    if (e->cfg.use_cuda_graph) {
+    if (e->cfg.use_cuda_graph && p->eager_runs > 0) {
       auto it = p->graphs.find(out_channels);
       if (it == p->graphs.end()) {
         cudaStream_t cs;
@@ -997,6 +998,7 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
       GP_CUDA(cudaGraphLaunch(it->second, s));
     } else {
       GP_CUDA(run_ops(p, GP_STAGE_VAE_ENCODE, GP_STAGE_READOUT, out_channels, s));
+      p->eager_runs++;
     }
     GP_CUDA(cudaMemcpyAsync(out, p->out_f32, npix * out_channels * 4, out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
     if (rgb_on_host || out_on_host) GP_CUDA(cudaStreamSynchronize(s));

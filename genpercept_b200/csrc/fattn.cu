@@ -7,10 +7,15 @@
 //   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T (128x128x64, TMEM, double buffered);
 //                                   O_j = P_j V_j (128x64x128, fresh TMEM tile, double buffered)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : softmax       — one query row per thread: two passes over the S row in TMEM
-//                                   (max, then exp2 / sum), P_j written as 16-bit into shared memory
-//                                   in the K-major SWIZZLE_128B operand layout, O accumulated in
-//                                   registers:  O <- (O + O_{j-1}) * 2^{(m_{j-1} - m_j)}.
+//   warps 4..11   : softmax       — TWO threads per query row (warps w and w+4 share TMEM lanes
+//                                   32*(w%4)..+31): each owns 64 of the 128 key columns of S_j and 32
+//                                   of the 64 output columns.  Two passes over the S half-row in TMEM
+//                                   (max, then exp2 / sum); the row maximum is exchanged through
+//                                   shared memory once per block; P_j is written 16-bit into shared
+//                                   memory in the K-major SWIZZLE_128B operand layout; O is
+//                                   accumulated in registers: O <- (O + O_{j-1}) * 2^{m_{j-1} - m_j}.
+//   Two softmax warps per SM sub-partition hide the ALU/MUFU/TMEM latencies that a single warp per
+//   sub-partition left exposed (ncu r1c: issue slots 47 % busy, tensor pipe 17 %).
 //
 // S and P never touch HBM (the round-1 unfused path wrote both: 4 x T^2 x 2 bytes per head).
 #include "fattn.h"
@@ -23,13 +28,14 @@
 namespace gp {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kStages = 3;
 constexpr int kQBytes = 128 * 64 * 2;          // 16 KiB
 constexpr int kKBytes = 128 * 64 * 2;          // 16 KiB
 constexpr int kVBytes = 64 * 128 * 2;          // 16 KiB (two 64-key sub-tiles of 8 KiB)
 constexpr int kPBytes = 128 * 128 * 2;         // 32 KiB (two 64-key sub-tiles of 16 KiB)
-constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
+constexpr int kXchgBytes = 2 * 2 * 128 * 4;    // row-max exchange [parity][half][row] + reused for row sums
+constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + kXchgBytes + 256 + 1024;
 constexpr int kTmemCols = 512;
 constexpr int kOCol = 256;                     // S0: [0,128) S1: [128,256) O0: [256,320) O1: [320,384)
 
@@ -51,6 +57,9 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void pair_sync(int id) {   // the two warps that share a 32-row slice
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constant__ FattnParams p) {
@@ -60,7 +69,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
   uint8_t* sK = sQ + kQBytes;                       // [stage][16 KiB]
   uint8_t* sV = sK + kStages * kKBytes;             // [stage][16 KiB]
   uint8_t* sP = sV + kStages * kVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  float* xchg = reinterpret_cast<float*>(sP + kPBytes);          // [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes + kXchgBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                     // [3]
   uint64_t* kv_empty = bars + 4;                    // [3]
@@ -83,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&o_full[i], 1); }
-    mbar_init(p_full, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&o_full[i], 1); }
+    mbar_init(p_full, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -143,71 +153,67 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output
-    const int wq = warp - 4;
+    const int half = (warp - 4) >> 2;          // which 64 key columns / 32 output columns
+    const int wq = (warp - 4) & 3;             // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const float c2 = p.scale_log2e;
     float m = -INFINITY, l = 0.f;
-    float O[64];
+    float O[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) O[i] = 0.f;
-    uint8_t* prow = sP + row * 128;
+    for (int i = 0; i < 32; ++i) O[i] = 0.f;
+    uint8_t* prow = sP + half * 16384 + row * 128;       // this thread's 64-key sub-tile row
     const int sw = row & 7;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1, 15);
       tc_fence_after();
-      const uint32_t ts = tmem_base + lane_off + (j & 1) * 128;
-      const int kvalid = min(128, T - j * 128);
-      // pass 1: row maximum.  One warp per SM sub-partition runs this, so ALU latency is only hidden
-      // by instruction-level parallelism: 4 independent max chains, TMEM loads one chunk ahead.
+      const uint32_t ts = tmem_base + lane_off + (j & 1) * 128 + half * 64;
+      const int kvalid = min(128, T - j * 128) - half * 64;   // valid columns among this thread's 64
       uint32_t ra[32], rb[32];
-      float mx0 = m, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      // pass 1: maximum over this thread's 64 columns, then exchange with the partner thread
       tmem_ld_32x32(ts, ra);
+      tmem_ld_32x32(ts + 32, rb);
+      tmem_ld_wait();
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (kvalid >= 64) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        uint32_t* cur = (c & 1) ? rb : ra;
-        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
-        if (kvalid == 128) {
+        for (int q = 0; q < 32; q += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[q]), __uint_as_float(rb[q])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(ra[q + 1]), __uint_as_float(rb[q + 1])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(ra[q + 2]), __uint_as_float(rb[q + 2])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(ra[q + 3]), __uint_as_float(rb[q + 3])));
+        }
+      } else {
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
-            mx1 = fmaxf(mx1, __uint_as_float(cur[q + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(cur[q + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(cur[q + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) if (c * 32 + q < kvalid) mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
+        for (int q = 0; q < 32; ++q) {
+          if (q < kvalid) mx0 = fmaxf(mx0, __uint_as_float(ra[q]));
+          if (32 + q < kvalid) mx1 = fmaxf(mx1, __uint_as_float(rb[q]));
         }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xs = xchg + (j & 1) * 256;
+      xs[half * 128 + row] = mx;
+      pair_sync(1 + wq);
+      mx = fmaxf(m, fmaxf(mx, xs[(half ^ 1) * 128 + row]));
       const float alpha = ex2((m - mx) * c2);
       if (j > 0) {
         mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1, 16);
         tc_fence_after();
-        const uint32_t to = tmem_base + lane_off + kOCol + ((j - 1) & 1) * 64;
+        uint32_t ro[32];
+        tmem_ld_32x32(tmem_base + lane_off + kOCol + ((j - 1) & 1) * 64 + half * 32, ro);
+        tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r[32];
-          tmem_ld_32x32(to + h * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 32; ++q) O[h * 32 + q] = (O[h * 32 + q] + __uint_as_float(r[q])) * alpha;
-        }
+        for (int q = 0; q < 32; ++q) O[q] = (O[q] + __uint_as_float(ro[q])) * alpha;
       }
       l *= alpha;
-      // pass 2: probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
+      // pass 2: probabilities -> shared memory (A operand of P.V), partial row sum
       const float mb = mx * c2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      tmem_ld_32x32(ts, ra);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        uint32_t* cur = (c & 1) ? rb : ra;
-        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t* cur = c ? rb : ra;
         float pv[32];
-        if (kvalid == 128) {
+        if (kvalid >= 64) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) pv[q] = ex2(__uint_as_float(cur[q]) * c2 - mb);
         } else {
@@ -216,7 +222,6 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         }
 #pragma unroll
         for (int q = 0; q < 32; q += 4) { l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3]; }
-        uint8_t* dst = prow + (c >> 1) * 16384;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
           u.y = pack16<BF16>(pv[8 * i + 2], pv[8 * i + 3]);
           u.z = pack16<BF16>(pv[8 * i + 4], pv[8 * i + 5]);
           u.w = pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]);
-          *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + i) ^ sw) << 4)) = u;
+          *reinterpret_cast<uint4*>(prow + (((c * 4 + i) ^ sw) << 4)) = u;
         }
       }
       l += (l0 + l1) + (l2 + l3);
@@ -234,26 +239,26 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       mbar_arrive(p_full);
       m = mx;
     }
-    // last partial product, normalise, store
+    // last partial product, total row sum (both halves), normalise, store
+    float* xs = xchg + (nblk & 1) * 256;
+    xs[half * 128 + row] = l;
     mbar_wait(&o_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1, 17);
     tc_fence_after();
+    pair_sync(1 + wq);
+    const float inv = 1.f / (l + xs[(half ^ 1) * 128 + row]);
     {
-      const uint32_t to = tmem_base + lane_off + kOCol + ((nblk - 1) & 1) * 64;
-      const float inv = 1.f / l;
+      uint32_t ro[32];
+      tmem_ld_32x32(tmem_base + lane_off + kOCol + ((nblk - 1) & 1) * 64 + half * 32, ro);
+      tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r[32];
-        tmem_ld_32x32(to + h * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) O[h * 32 + q] = (O[h * 32 + q] + __uint_as_float(r[q])) * inv;
-      }
+      for (int q = 0; q < 32; ++q) O[q] = (O[q] + __uint_as_float(ro[q])) * inv;
     }
     const int qrow = qt * 128 + row;
     if (qrow < T) {
-      uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.out_b_stride + (long long)qrow * p.out_row_stride + head * 64;
+      uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.out_b_stride +
+                     (long long)qrow * p.out_row_stride + head * 64 + half * 32;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 u;
         u.x = pack16<BF16>(O[8 * i + 0], O[8 * i + 1]);
         u.y = pack16<BF16>(O[8 * i + 2], O[8 * i + 3]);
