@@ -1,21 +1,22 @@
 // Fused self-attention forward for head_dim 64 (the SD-2.1 UNet's BasicTransformerBlock.attn1):
 //   O = softmax(Q K^T) V   per (image, head), non-causal, fp32 softmax state, 16-bit operands.
-// (Softmax scale is folded into Wq at load.)  FlashAttention-style online softmax on tcgen05:
+// (Softmax scale is folded into Wq at load.)  FlashAttention-style online softmax on tcgen05, with
+// TWO 128-row query tiles per CTA that ping-pong on the tensor pipe and share every K/V block:
 //
-//   warp 0 lane 0 : TMA producer  — Q tile once; K block [128 keys x 64] + V^T block [64 x 128 keys]
-//                                   per iteration into a 3-stage ring
-//   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T (128x128x64, TMEM, double buffered);
-//                                   O_j = P_j V_j (128x64x128, fresh TMEM tile, double buffered)
-//   warp 2        : TMEM allocator
-//   warps 4..11   : softmax       — TWO threads per query row (warps w and w+4 share TMEM lanes
-//                                   32*(w%4)..+31): each owns 64 of the 128 key columns of S_j and 32
-//                                   of the 64 output columns.  Two passes over the S half-row in TMEM
-//                                   (max, then exp2 / sum); the row maximum is exchanged through
-//                                   shared memory once per block; P_j is written 16-bit into shared
-//                                   memory in the K-major SWIZZLE_128B operand layout; O is
-//                                   accumulated in registers: O <- (O + O_{j-1}) * 2^{m_{j-1} - m_j}.
-//   Two softmax warps per SM sub-partition hide the ALU/MUFU/TMEM latencies that a single warp per
-//   sub-partition left exposed (ncu r1c: issue slots 47 % busy, tensor pipe 17 %).
+//   warp 0 lane 0 : TMA producer  — both Q tiles once; K block [128 keys x 64] + V^T block
+//                                   [64 x 128 keys] per iteration into a 4-stage ring
+//   warp 1 lane 0 : MMA issuer    — per tile t and block j:  S_t = Q_t K_j^T (128x128x64, one TMEM
+//                                   buffer per tile);  O_t,j = P_t,j V_j (128x64x128, fresh TMEM tile,
+//                                   double buffered)
+//   warp 2        : TMEM allocator (512 columns: S_A, S_B, O_A[2], O_B[2])
+//   warps 4..7    : softmax of tile A, warps 8..11 : softmax of tile B — one query row per thread:
+//                   two passes over the S row in TMEM (max, then exp2 / sum), P written 16-bit into
+//                   shared memory in the K-major SWIZZLE_128B operand layout, O accumulated in
+//                   registers:  O <- (O + O_{j-1}) * 2^{m_{j-1} - m_j}.
+// Every SM sub-partition hosts one softmax warp of each tile, so while tile A waits on its MMA /
+// TMEM / MUFU latencies tile B computes (ncu r1c/r1d: a single tile left issue slots < 50 % busy and
+// the tensor pipe at 17 %).  The kernel is MUFU-bound by construction: 128x128 exp2 per 512 tensor
+// cycles at 16 exp2/clk/SM.
 //
 // S and P never touch HBM (the round-1 unfused path wrote both: 4 x T^2 x 2 bytes per head).
 #include "fattn.h"
@@ -29,15 +30,14 @@ namespace gp {
 namespace {
 
 constexpr int kThreads = 384;
-constexpr int kStages = 3;
-constexpr int kQBytes = 128 * 64 * 2;          // 16 KiB
+constexpr int kStages = 4;
+constexpr int kQBytes = 128 * 64 * 2;          // 16 KiB per tile
 constexpr int kKBytes = 128 * 64 * 2;          // 16 KiB
 constexpr int kVBytes = 64 * 128 * 2;          // 16 KiB (two 64-key sub-tiles of 8 KiB)
-constexpr int kPBytes = 128 * 128 * 2;         // 32 KiB (two 64-key sub-tiles of 16 KiB)
-constexpr int kXchgBytes = 2 * 2 * 128 * 4;    // row-max exchange [parity][half][row] + reused for row sums
-constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + kXchgBytes + 256 + 1024;
+constexpr int kPBytes = 128 * 128 * 2;         // 32 KiB per tile (two 64-key sub-tiles of 16 KiB)
+constexpr int kSmemBytes = 2 * kQBytes + kStages * (kKBytes + kVBytes) + 2 * kPBytes + 256 + 1024;
 constexpr int kTmemCols = 512;
-constexpr int kOCol = 256;                     // S0: [0,128) S1: [128,256) O0: [256,320) O1: [320,384)
+constexpr int kOCol = 256;                     // S_A [0,128) S_B [128,256) O_t[buf] at 256 + t*128 + buf*64
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -57,35 +57,35 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void pair_sync(int id) {   // the two warps that share a 32-row slice
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constant__ FattnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;                       // [stage][16 KiB]
+  uint8_t* sQ = smem;                               // [tile][16 KiB]
+  uint8_t* sK = sQ + 2 * kQBytes;                   // [stage][16 KiB]
   uint8_t* sV = sK + kStages * kKBytes;             // [stage][16 KiB]
-  uint8_t* sP = sV + kStages * kVBytes;
-  float* xchg = reinterpret_cast<float*>(sP + kPBytes);          // [2][2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes + kXchgBytes);
+  uint8_t* sP = sV + kStages * kVBytes;             // [tile][32 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                     // [3]
-  uint64_t* kv_empty = bars + 4;                    // [3]
-  uint64_t* s_full = bars + 7;                      // [2]
-  uint64_t* s_empty = bars + 9;                     // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_full = bars + 12;                     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 1;                     // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;           // [kStages]
+  uint64_t* s_full = kv_empty + kStages;            // [tile]
+  uint64_t* p_full = s_full + 2;                    // [tile]
+  uint64_t* o_full = p_full + 2;                    // [tile][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.q_tiles;
-  const int bh = blockIdx.x / p.q_tiles;
+  const int pairs = (p.q_tiles + 1) >> 1;
+  const int qp = blockIdx.x % pairs;
+  const int bh = blockIdx.x / pairs;
   const int head = bh % p.heads, b = bh / p.heads;
   const int T = p.T;
   const int nblk = (T + 127) >> 7;
+  const int ntile = (2 * qp + 1 < p.q_tiles) ? 2 : 1;   // the last pair of an odd tile count is half empty
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&o_full[i], 1); }
-    mbar_init(p_full, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
+    for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
-    mbar_expect_tx(q_full, kQBytes);
-    tma_load_3d(sQ, &p.tmQ, q_full, head * 64, qt * 128, b);
+    mbar_expect_tx(q_full, (uint32_t)(ntile * kQBytes));
+    for (int t = 0; t < ntile; ++t) tma_load_3d(sQ + t * kQBytes, &p.tmQ, q_full, head * 64, (2 * qp + t) * 128, b);
     for (int j = 0; j < nblk; ++j) {
       const int st = j % kStages;
       mbar_wait(&kv_empty[st], ((j / kStages) & 1) ^ 1, 10);
@@ -119,101 +119,109 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);
     const uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0);
-    const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ));
-    auto mma_s = [&](int j) {
+    auto mma_s = [&](int t, int j) {          // S_t = Q_t K_j^T ; caller guarantees kv_full(j) was observed
       const int st = j % kStages;
-      mbar_wait(&kv_full[st], (j / kStages) & 1, 11);
-      tc_fence_after();
+      const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ + t * kQBytes));
       const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK + st * kKBytes));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + (j & 1) * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k ? 1u : 0u);
-      umma_commit(&s_full[j & 1]);
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k ? 1u : 0u);
+      umma_commit(&s_full[t]);
     };
-    mbar_wait(q_full, 0, 12);
-    tc_fence_after();
-    mma_s(0);
-    if (nblk > 1) mma_s(1);
-    for (int j = 0; j < nblk; ++j) {
+    auto mma_o = [&](int t, int j) {          // O_t[j&1] = P_t V_j
       const int st = j % kStages;
-      mbar_wait(p_full, j & 1, 13);
-      tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
-        const uint64_t a = make_sw128_kmajor_desc(smem_u32(sP + (kk >> 2) * 16384)) + 2 * (kk & 3);
+        const uint64_t a = make_sw128_kmajor_desc(smem_u32(sP + t * kPBytes + (kk >> 2) * 16384)) + 2 * (kk & 3);
         const uint64_t bd = make_sw128_kmajor_desc(smem_u32(sV + st * kVBytes + (kk >> 2) * 8192)) + 2 * (kk & 3);
-        umma_f16(tmem_base + kOCol + (j & 1) * 64, a, bd, idesc_o, kk ? 1u : 0u);
+        umma_f16(tmem_base + kOCol + t * 128 + (j & 1) * 64, a, bd, idesc_o, kk ? 1u : 0u);
       }
-      umma_commit(&o_full[j & 1]);
-      umma_commit(&kv_empty[st]);
-      if (j + 2 < nblk) {
-        mbar_wait(&s_empty[j & 1], (j >> 1) & 1, 14);
+      umma_commit(&o_full[t * 2 + (j & 1)]);
+    };
+    mbar_wait(q_full, 0, 12);
+    mbar_wait(&kv_full[0], 0, 11);
+    tc_fence_after();
+    for (int t = 0; t < ntile; ++t) mma_s(t, 0);
+    for (int j = 0; j < nblk; ++j) {
+      const bool more = j + 1 < nblk;
+      if (more) {
+        mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1, 11);
         tc_fence_after();
-        mma_s(j + 2);
+      }
+      for (int t = 0; t < ntile; ++t) {
+        mbar_wait(&p_full[t], j & 1, 13);     // P_t,j is in shared memory and S_t has been consumed
+        tc_fence_after();
+        mma_o(t, j);
+        if (t == ntile - 1) umma_commit(&kv_empty[j % kStages]);   // every consumer of block j has been issued
+        if (more) mma_s(t, j + 1);
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax + output
-    const int half = (warp - 4) >> 2;          // which 64 key columns / 32 output columns
+  } else if (warp >= 4 && (warp - 4) / 4 < ntile) {
+    // ------------------------------------------------------------------ softmax + output of tile t
+    const int t = (warp - 4) >> 2;
     const int wq = (warp - 4) & 3;             // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const float c2 = p.scale_log2e;
     float m = -INFINITY, l = 0.f;
-    float O[32];
+    float O[64];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) O[i] = 0.f;
-    uint8_t* prow = sP + half * 16384 + row * 128;       // this thread's 64-key sub-tile row
+    for (int i = 0; i < 64; ++i) O[i] = 0.f;
+    const uint32_t prow = smem_u32(sP + t * kPBytes) + row * 128;
     const int sw = row & 7;
+    const uint32_t ts = tmem_base + lane_off + t * 128;
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1, 15);
+      mbar_wait(&s_full[t], j & 1, 15);
       tc_fence_after();
-      const uint32_t ts = tmem_base + lane_off + (j & 1) * 128 + half * 64;
-      const int kvalid = min(128, T - j * 128) - half * 64;   // valid columns among this thread's 64
+      const int kvalid = min(128, T - j * 128);
       uint32_t ra[32], rb[32];
-      // pass 1: maximum over this thread's 64 columns, then exchange with the partner thread
+      // pass 1: row maximum (4 independent chains, TMEM loads one chunk ahead)
+      float mx0 = m, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       tmem_ld_32x32(ts, ra);
-      tmem_ld_32x32(ts + 32, rb);
-      tmem_ld_wait();
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if (kvalid >= 64) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[q]), __uint_as_float(rb[q])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(ra[q + 1]), __uint_as_float(rb[q + 1])));
-          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(ra[q + 2]), __uint_as_float(rb[q + 2])));
-          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(ra[q + 3]), __uint_as_float(rb[q + 3])));
-        }
-      } else {
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? rb : ra;
+        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
+        if (kvalid == 128) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          if (q < kvalid) mx0 = fmaxf(mx0, __uint_as_float(ra[q]));
-          if (32 + q < kvalid) mx1 = fmaxf(mx1, __uint_as_float(rb[q]));
+          for (int q = 0; q < 32; q += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
+            mx1 = fmaxf(mx1, __uint_as_float(cur[q + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(cur[q + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(cur[q + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) if (c * 32 + q < kvalid) mx0 = fmaxf(mx0, __uint_as_float(cur[q]));
         }
       }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      float* xs = xchg + (j & 1) * 256;
-      xs[half * 128 + row] = mx;
-      pair_sync(1 + wq);
-      mx = fmaxf(m, fmaxf(mx, xs[(half ^ 1) * 128 + row]));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float alpha = ex2((m - mx) * c2);
+      tmem_ld_32x32(ts, ra);                       // first chunk of pass 2, in flight during the O update
       if (j > 0) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1, 16);
+        mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 16);
         tc_fence_after();
-        uint32_t ro[32];
-        tmem_ld_32x32(tmem_base + lane_off + kOCol + ((j - 1) & 1) * 64 + half * 32, ro);
+        const uint32_t to = tmem_base + lane_off + kOCol + t * 128 + ((j - 1) & 1) * 64;
+        tmem_ld_32x32(to, rb);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) O[q] = (O[q] + __uint_as_float(ro[q])) * alpha;
+        for (int q = 0; q < 32; ++q) O[q] = (O[q] + __uint_as_float(rb[q])) * alpha;
+        tmem_ld_32x32(to + 32, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) O[32 + q] = (O[32 + q] + __uint_as_float(rb[q])) * alpha;
       }
       l *= alpha;
-      // pass 2: probabilities -> shared memory (A operand of P.V), partial row sum
+      // pass 2: probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
       const float mb = mx * c2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t* cur = c ? rb : ra;
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? rb : ra;
+        if (c < 3) tmem_ld_32x32(ts + (c + 1) * 32, (c & 1) ? ra : rb);
         float pv[32];
-        if (kvalid >= 64) {
+        if (kvalid == 128) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) pv[q] = ex2(__uint_as_float(cur[q]) * c2 - mb);
         } else {
@@ -222,43 +230,40 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         }
 #pragma unroll
         for (int q = 0; q < 32; q += 4) { l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3]; }
+        const uint32_t dst = prow + (c >> 1) * 16384;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack16<BF16>(pv[8 * i + 0], pv[8 * i + 1]);
-          u.y = pack16<BF16>(pv[8 * i + 2], pv[8 * i + 3]);
-          u.z = pack16<BF16>(pv[8 * i + 4], pv[8 * i + 5]);
-          u.w = pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]);
-          *reinterpret_cast<uint4*>(prow + (((c * 4 + i) ^ sw) << 4)) = u;
-        }
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(dst + ((((c & 1) * 4 + i) ^ sw) << 4), pack16<BF16>(pv[8 * i + 0], pv[8 * i + 1]),
+                       pack16<BF16>(pv[8 * i + 2], pv[8 * i + 3]), pack16<BF16>(pv[8 * i + 4], pv[8 * i + 5]),
+                       pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
       l += (l0 + l1) + (l2 + l3);
-      tc_fence_before();
-      mbar_arrive(&s_empty[j & 1]);
-      fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      tc_fence_before();                          // S_t reads are complete before the MMA warp overwrites it
+      fence_proxy_async_smem();                   // P_t visible to the tensor core (async proxy)
+      mbar_arrive(&p_full[t]);
       m = mx;
     }
-    // last partial product, total row sum (both halves), normalise, store
-    float* xs = xchg + (nblk & 1) * 256;
-    xs[half * 128 + row] = l;
-    mbar_wait(&o_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1, 17);
+    // last partial product, normalise, store
+    mbar_wait(&o_full[t * 2 + ((nblk - 1) & 1)], ((nblk - 1) >> 1) & 1, 17);
     tc_fence_after();
-    pair_sync(1 + wq);
-    const float inv = 1.f / (l + xs[(half ^ 1) * 128 + row]);
     {
-      uint32_t ro[32];
-      tmem_ld_32x32(tmem_base + lane_off + kOCol + ((nblk - 1) & 1) * 64 + half * 32, ro);
-      tmem_ld_wait();
+      const uint32_t to = tmem_base + lane_off + kOCol + t * 128 + ((nblk - 1) & 1) * 64;
+      const float inv = 1.f / l;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) O[q] = (O[q] + __uint_as_float(ro[q])) * inv;
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld_32x32(to + h * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) O[h * 32 + q] = (O[h * 32 + q] + __uint_as_float(r[q])) * inv;
+      }
     }
-    const int qrow = qt * 128 + row;
+    const int qrow = (2 * qp + t) * 128 + row;
     if (qrow < T) {
       uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.out_b_stride +
-                     (long long)qrow * p.out_row_stride + head * 64 + half * 32;
+                     (long long)qrow * p.out_row_stride + head * 64;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         uint4 u;
         u.x = pack16<BF16>(O[8 * i + 0], O[8 * i + 1]);
         u.y = pack16<BF16>(O[8 * i + 2], O[8 * i + 3]);
@@ -288,7 +293,7 @@ cudaError_t fattn_launch(const FattnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = p.B * p.heads * p.q_tiles;
+  const int grid = p.B * p.heads * ((p.q_tiles + 1) / 2);
   if (grid <= 0) return cudaSuccess;
   if (p.bf16)
     fattn_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
