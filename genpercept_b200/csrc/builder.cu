@@ -56,6 +56,11 @@ void Arena::release(size_t off) {
 }
 
 // ------------------------------------------------------------------------------------ Builder
+Builder::Builder(bool bf16, bool measuring, uint8_t* base) : bf16_(bf16), measuring_(measuring), base_(base) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    num_sms = n;
+}
 T4 Builder::alloc(int N, int H, int W, int C) {
   T4 t;
   t.N = N; t.H = H; t.W = W; t.C = C;
@@ -68,7 +73,14 @@ T4 Builder::external(const void* p, int N, int H, int W, int C) const {
   t.off = (long long)(reinterpret_cast<const uint8_t*>(p) - base_);
   return t;
 }
-void Builder::release(const T4& t) { arena_.release((size_t)t.off); }
+void Builder::release(const T4& t) {
+  auto it = stats.find(t.off);
+  if (it != stats.end()) {
+    arena_.release(it->second.off);
+    stats.erase(it);
+  }
+  arena_.release((size_t)t.off);
+}
 
 void Builder::push(const std::string& name, int launches, double flops, double bytes,
                    std::function<cudaError_t(cudaStream_t)> fn) {
@@ -136,6 +148,21 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   if (a.res1) bytes += (double)a.res1->bytes();
   if (a.res2) bytes += (double)a.res2->bytes();
   if (!a.out_f32) GP_REQUIRE(a.out.N == N && a.out.H == Ho && a.out.W == Wo, name + ": output shape mismatch");
+  // GroupNorm partial sums from the epilogue: same decision (and arena allocation) in both passes
+  const bool tokens_mode = (a.ks == 1 && a.mode == 0 && a.sc.empty() && a.srcs.size() == 1 && !a.out_f32);
+  const int bn_pre = choose_bn(Cout, a.force_bn);
+  const long long work_px = tokens_mode ? (long long)N * H * W
+                                        : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
+  const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+  bool emit_stats = a.want_stats && !a.out_f32 && !(a.flags & IG_GEGLU) && Cout == a.out.C && Cout <= 512;
+  if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
+  size_t stats_off = 0;
+  const size_t stats_bytes = (size_t)N * num_sms * Cout * 2 * sizeof(float);
+  if (emit_stats) {
+    GP_REQUIRE(stats.find(a.out.off) == stats.end(), name + ": output already has statistics");
+    stats_off = arena_.alloc(stats_bytes);
+    stats[a.out.off] = StatsInfo{stats_off, num_sms, Cout};
+  }
   if (measuring_) return;
 
   IgemmParams p;
@@ -149,7 +176,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   p.BN = choose_bn(Cout, a.force_bn);
   p.Z1 = 1; p.Z0 = 1;
   p.out_sy = p.out_sx = 1;
-  const bool tokens = (a.ks == 1 && a.mode == 0 && a.sc.empty() && a.srcs.size() == 1 && !a.out_f32);
+  const bool tokens = tokens_mode;
   if (tokens) {
     const long long ntok = (long long)N * H * W;
     GP_REQUIRE(ntok < (1LL << 31), name + ": too many tokens");
@@ -239,13 +266,28 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   }
   check_cuda(make_tmap_b(&p.tmB, a.w->w, a.w->ktot, a.w->rows, a.w->nz, a.w->ktot, (long long)a.w->rows * a.w->ktot,
                          p.BN, bf16_), name + ": tmap B");
+  if (emit_stats) {
+    p.stats = reinterpret_cast<float*>(raw_ptr(stats_off));
+    p.stats_slots = num_sms;
+    p.stats_hw = tokens ? H * W : 0;
+  }
   finalize_or_throw(&p, name);
+  GP_REQUIRE(p.MT == mt_pre && p.BN == bn_pre, name + ": tile pre-selection disagrees with the plan");
   const int ncls = p.cls_from_z0 ? p.Z0 : 1;
   for (int c = 0; c < ncls; ++c)
     GP_REQUIRE(p.nkb[c] * 64 == a.w->ktot, name + ": packed K (" + std::to_string(a.w->ktot) + ") != planned K (" +
                                               std::to_string(p.nkb[c] * 64) + ")");
   GP_REQUIRE(a.w->rows >= Cout || a.w->rows == Cout, name + ": packed rows < Cout");
-  push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
+  if (emit_stats) {
+    float* sp = p.stats;
+    push(name, 2, flops, bytes, [p, sp, stats_bytes](cudaStream_t s) {
+      cudaError_t e = cudaMemsetAsync(sp, 0, stats_bytes, s);
+      if (e != cudaSuccess) return e;
+      return igemm_launch(p, s);
+    });
+  } else {
+    push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
+  }
   ops.back().kind = 1;
 }
 
@@ -380,35 +422,50 @@ void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const Nor
                  bool silu, const T4& out) {
   int ctot = 0;
   for (auto& s : srcs) ctot += s.C;
-  GP_REQUIRE(ctot == out.C && nw.C == ctot && ctot % groups == 0, name + ": GroupNorm channel mismatch");
+  GP_REQUIRE(ctot == out.C && nw.C == ctot && ctot % groups == 0 && srcs.size() <= 2, name + ": GroupNorm channel mismatch");
   const int N = out.N;
   const long long HW = (long long)out.H * out.W;
   const int chunks = gn_chunks(N, HW);
-  const size_t part_off = arena_.alloc((size_t)N * chunks * ctot * 2 * sizeof(float));
+  // per source: partial sums either already produced by the conv that wrote it, or computed here
+  std::vector<size_t> own(srcs.size(), (size_t)-1);
+  std::vector<GnSrc> gs(srcs.size());
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    auto it = stats.find(srcs[i].off);
+    if (it != stats.end() && it->second.C == srcs[i].C) {
+      gs[i] = GnSrc{measuring_ ? nullptr : reinterpret_cast<const float*>(raw_ptr(it->second.off)), it->second.slots, srcs[i].C};
+    } else {
+      own[i] = arena_.alloc((size_t)N * chunks * srcs[i].C * 2 * sizeof(float));
+      gs[i] = GnSrc{measuring_ ? nullptr : reinterpret_cast<const float*>(raw_ptr(own[i])), chunks, srcs[i].C};
+    }
+  }
   if (!measuring_) {
-    float* partial = reinterpret_cast<float*>(raw_ptr(part_off));
     float* ss = gn_ss;
     const bool bf = bf16_;
     std::vector<const void*> xs;
     std::vector<int> cs;
-    for (auto& s : srcs) { xs.push_back(ptr(s)); cs.push_back(s.C); }
+    std::vector<bool> need;
+    int launches = 1;
+    double bytes = (double)out.bytes();
+    for (size_t i = 0; i < srcs.size(); ++i) {
+      xs.push_back(ptr(srcs[i]));
+      cs.push_back(srcs[i].C);
+      need.push_back(own[i] != (size_t)-1);
+      bytes += (need[i] ? 2.0 : 1.0) * srcs[i].bytes();
+      launches += need[i] ? 2 : 1;
+    }
     void* y = ptr(out);
     const float* gamma = nw.gamma;
     const float* beta = nw.beta;
-    double bytes = 0;
-    for (auto& s : srcs) bytes += 2.0 * s.bytes();
-    bytes += (double)out.bytes();
-    push(name, 1 + 2 * (int)srcs.size(), 0, bytes, [=](cudaStream_t s) {
+    push(name, launches, 0, bytes, [=](cudaStream_t s) {
       cudaError_t e;
-      int coff = 0;
       for (size_t i = 0; i < xs.size(); ++i) {
-        e = gn_stats(xs[i], N, HW, cs[i], partial, chunks, ctot, coff, bf, s);
+        if (!need[i]) continue;
+        e = gn_stats(xs[i], N, HW, cs[i], const_cast<float*>(gs[i].partial), chunks, cs[i], 0, bf, s);
         if (e != cudaSuccess) return e;
-        coff += cs[i];
       }
-      e = gn_finalize(partial, chunks, gamma, beta, N, ctot, groups, HW, eps, ss, s);
+      e = gn_finalize(gs.data(), (int)gs.size(), gamma, beta, N, ctot, groups, HW, eps, ss, s);
       if (e != cudaSuccess) return e;
-      coff = 0;
+      int coff = 0;
       for (size_t i = 0; i < xs.size(); ++i) {
         e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s);
         if (e != cudaSuccess) return e;
@@ -417,7 +474,8 @@ void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const Nor
       return cudaSuccess;
     });
   }
-  arena_.release(part_off);
+  for (size_t i = 0; i < srcs.size(); ++i)
+    if (own[i] != (size_t)-1) arena_.release(own[i]);
 }
 
 void Builder::ln(const std::string& name, const T4& x, const NormW& nw, float eps, const T4& out) {

@@ -380,6 +380,7 @@ struct gp_engine {
     c.srcs = {src8};
     c.w = &conv_w(key, {cin});
     c.out = out;
+    c.want_stats = true;
     b.conv(key, c);
   }
 
@@ -398,6 +399,7 @@ struct gp_engine {
       c.srcs = {a};
       c.w = &conv_w(p + ".conv1", {cin}, "", {}, tp.empty() ? nullptr : &tp);
       c.out = h;
+      c.want_stats = true;     // feeds norm2
       b.conv(p + ".conv1", c);
     }
     b.release(a);
@@ -409,6 +411,7 @@ struct gp_engine {
       ConvArgs c;
       c.srcs = {a2};
       c.out = out;
+      c.want_stats = true;     // resnet outputs feed the next GroupNorm (norm1 / transformer norm / conv_norm_out)
       if (cin != cout) {
         c.sc = xs;
         c.w = &conv_w(p + ".conv2", {cout}, p + ".conv_shortcut", cs);
@@ -454,18 +457,33 @@ struct gp_engine {
     // feed-forward (GEGLU)
     T4 l3 = b.alloc(x.N, x.H, x.W, C);
     b.ln(blk + ".norm3", t2, norm_w(blk + ".norm3"), 1e-5f, l3);
-    T4 ff = b.alloc(x.N, x.H, x.W, 8 * C);
-    { ConvArgs c; c.srcs = {l3}; c.ks = 1; c.w = &lin_w(blk + ".ff.net.0.proj"); c.out = ff; b.conv(blk + ".ff.proj", c); }
-    b.release(l3);
+    // GEGLU fused into the projection's epilogue: weight rows interleaved [16 values | 16 gates] per
+    // 32-column chunk so one thread holds a value and its gate; the 8C-wide tensor is never written.
+    if (!packed.count(blk + ".ff.geglu_w")) {
+      const HostT &w = T(blk + ".ff.net.0.proj.weight"), &bb = T(blk + ".ff.net.0.proj.bias");
+      const int C4 = 4 * C;
+      std::vector<float> m((size_t)8 * C * C), bias(8 * C);
+      for (int r = 0; r < 8 * C; ++r) {
+        const int chunk = r / 32, q = r % 32;
+        const int src = q < 16 ? chunk * 16 + q : C4 + chunk * 16 + (q - 16);
+        std::memcpy(&m[(size_t)r * C], &w.d[(size_t)src * C], (size_t)C * sizeof(float));
+        bias[r] = bb.d[src];
+      }
+      mat_w(blk + ".ff.geglu_w", 8 * C, C, m.data(), bias);
+    }
     T4 gg = b.alloc(x.N, x.H, x.W, 4 * C);
-    b.geglu_op(blk + ".ff.geglu", ff, gg);
-    b.release(ff);
+    {
+      ConvArgs c; c.srcs = {l3}; c.ks = 1; c.w = &packed.at(blk + ".ff.geglu_w"); c.out = gg; c.cout_valid = 8 * C;
+      c.flags = IG_GEGLU; c.force_bn = 256;
+      b.conv(blk + ".ff.proj_geglu", c);
+    }
+    b.release(l3);
     T4 t3 = b.alloc(x.N, x.H, x.W, C);
     { ConvArgs c; c.srcs = {gg}; c.ks = 1; c.w = &lin_w(blk + ".ff.net.2"); c.out = t3; c.res1 = &t2; b.conv(blk + ".ff.out", c); }
     b.release(gg);
     b.release(t2);
     T4 out = b.alloc(x.N, x.H, x.W, C);
-    { ConvArgs c; c.srcs = {t3}; c.ks = 1; c.w = &lin_w(p + ".proj_out"); c.out = out; c.res1 = &x; b.conv(p + ".proj_out", c); }
+    { ConvArgs c; c.srcs = {t3}; c.ks = 1; c.w = &lin_w(p + ".proj_out"); c.out = out; c.res1 = &x; c.want_stats = true; b.conv(p + ".proj_out", c); }
     b.release(t3);
     return out;
   }
@@ -497,7 +515,7 @@ struct gp_engine {
     b.attention(a, n, packed.at(a + ".to_qk"), lin_w(a + ".to_v", false), norms.at(a + ".to_v.biasbuf").gamma, 1, o);
     b.release(n);
     T4 y = b.alloc(r0.N, r0.H, r0.W, 512);
-    { ConvArgs c; c.srcs = {o}; c.ks = 1; c.w = &lin_w(a + ".to_out.0"); c.out = y; c.res1 = &r0; b.conv(a + ".to_out", c); }
+    { ConvArgs c; c.srcs = {o}; c.ks = 1; c.w = &lin_w(a + ".to_out.0"); c.out = y; c.res1 = &r0; c.want_stats = true; b.conv(a + ".to_out", c); }
     b.release(o);
     b.release(r0);
     T4 r1 = resnet(b, p + ".resnets.1", {y}, 512, 1e-6f, false);
@@ -520,7 +538,7 @@ struct gp_engine {
       if (i < 3) {
         const std::string k = e + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
         T4 y = b.alloc(x.N, (x.H + 1 - 3) / 2 + 1, (x.W + 1 - 3) / 2 + 1, x.C);
-        ConvArgs c; c.srcs = {x}; c.mode = 2; c.w = &conv_w(k, {x.C}); c.out = y;
+        ConvArgs c; c.srcs = {x}; c.mode = 2; c.w = &conv_w(k, {x.C}); c.out = y; c.want_stats = true;
         b.conv(k, c);
         b.release(x);
         x = y;
@@ -579,7 +597,7 @@ struct gp_engine {
       if (i < 3) {
         const std::string k = u + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
         T4 y = b.alloc(x.N, (x.H + 2 - 3) / 2 + 1, (x.W + 2 - 3) / 2 + 1, x.C);
-        ConvArgs c; c.srcs = {x}; c.mode = 1; c.w = &conv_w(k, {x.C}); c.out = y;
+        ConvArgs c; c.srcs = {x}; c.mode = 1; c.w = &conv_w(k, {x.C}); c.out = y; c.want_stats = true;
         b.conv(k, c);
         x = y;
         skips.push_back(x);
@@ -618,7 +636,7 @@ struct gp_engine {
         GP_REQUIRE(nxt.H == 2 * cur.H && nxt.W == 2 * cur.W, "input height/width must be multiples of 64");
         const std::string k = u + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
         T4 y = b.alloc(cur.N, 2 * cur.H, 2 * cur.W, cur.C);
-        ConvArgs c; c.srcs = {cur}; c.mode = 3; c.w = &conv_up_w(k); c.out = y;
+        ConvArgs c; c.srcs = {cur}; c.mode = 3; c.w = &conv_up_w(k); c.out = y; c.want_stats = true;
         b.conv(k, c);
         b.release(cur);
         cur = y;
@@ -683,7 +701,7 @@ struct gp_engine {
       if (i < 3) {
         const std::string k = d + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
         T4 y = b.alloc(x.N, 2 * x.H, 2 * x.W, x.C);
-        ConvArgs c; c.srcs = {x}; c.mode = 3; c.w = &conv_up_w(k); c.out = y;
+        ConvArgs c; c.srcs = {x}; c.mode = 3; c.w = &conv_up_w(k); c.out = y; c.want_stats = true;
         b.conv(k, c);
         b.release(x);
         x = y;

@@ -96,11 +96,12 @@ struct ConvArgs {
   int flags = 0;
   float* out_f32 = nullptr;   // fp32 NCHW destination [N, cout_valid, Ho, Wo]
   int force_bn = 0;
+  bool want_stats = false;    // let the epilogue emit GroupNorm partial sums of `out` (consumed by Builder::gn)
 };
 
 class Builder {
  public:
-  Builder(bool bf16, bool measuring, uint8_t* base) : bf16_(bf16), measuring_(measuring), base_(base) {}
+  Builder(bool bf16, bool measuring, uint8_t* base);
   T4 alloc(int N, int H, int W, int C);
   T4 external(const void* p, int N, int H, int W, int C) const;
   void release(const T4& t);
@@ -124,6 +125,10 @@ class Builder {
   void direct(const std::string& name, const T4& in, int cin, const DirectW& w, const T4& out, int flags,
               float* out_f32, int up);
   void custom(const std::string& name, int launches, double bytes, std::function<cudaError_t(cudaStream_t)> fn);
+
+  struct StatsInfo { size_t off; int slots; int C; };
+  std::map<long long, StatsInfo> stats;   // live tensors (by arena offset) whose producer emitted GN partial sums
+  int num_sms = 148;
 
   std::vector<Op> ops;
   int stage = 0;

@@ -74,6 +74,24 @@ __device__ __forceinline__ void add8(float* v, const uint4& u) {
   }
 }
 
+// Each lane holds 32 values v[0..32); on return lane i holds in v[0] the sum over all 32 lanes of
+// their v[i] (recursive halving: 16+8+4+2+1 = 31 shuffles, fixed order -> deterministic).
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+__device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -86,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sacc = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][Cout][2], only with p.stats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -194,11 +213,37 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const bool f32out = (p.flags & IG_OUT_F32_NCHW) != 0;
     const bool relu = (p.flags & IG_RELU) != 0;
     const bool aff = (p.flags & IG_AFFINE_CLAMP01) != 0;
+    const bool geglu = (p.flags & IG_GEGLU) != 0;
+    const bool do_stats = p.stats != nullptr;
+    const int etid = threadIdx.x - 128;        // 0..127 among the epilogue threads
+    int cur_img = -1;
+    // sum the four warp-private accumulators in a fixed order, publish this CTA's slot, reset
+    auto flush_stats = [&](int img) {
+      epi_sync();
+      float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
+      for (int i = etid; i < 2 * p.Cout; i += 128) {
+        const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
+        dst[i] = tot;
+        sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
+      }
+      epi_sync();
+    };
+    if (do_stats) {
+      for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
+      epi_sync();
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int cls = p.cls_from_z0 ? t.z0 : 0;
       const int n_base = t.n_tile * p.BN;
       bool waited = false;
+      if (do_stats) {
+        const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
+        if (img != cur_img) {
+          if (cur_img >= 0) flush_stats(cur_img);
+          cur_img = img;
+        }
+      }
       for (int h = 0; h < p.MT; ++h) {
         const int row = h * 128 + wq * 32 + lane;
         const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
@@ -251,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           uint32_t r[32];
           if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
           tmem_ld_wait();
-          if (!live) continue;
+          if (!live && !do_stats) continue;
           float v[32];
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           if (has1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r1[q]);
-          } else if (p.res1 != nullptr) {
+          } else if (p.res1 != nullptr && live) {
             const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res1) + off;
 #pragma unroll
             for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
@@ -279,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           if (has2) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r2[q]);
-          } else if (p.res2 != nullptr) {
+          } else if (p.res2 != nullptr && live) {
             const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res2) + off;
 #pragma unroll
             for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
@@ -287,6 +332,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           if (relu) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          if (geglu) {   // [16 values | 16 gates] -> 16 outputs at column n0/2 (weights are packed interleaved)
+            uint16_t* og = reinterpret_cast<uint16_t*>(p.out) + pix_off + (n0 >> 1);
+            float g[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) g[q] = v[q] * (0.5f * v[16 + q] * (1.f + erff(v[16 + q] * 0.70710678118654752f)));
+#pragma unroll
+            for (int q = 0; q < 16; q += 8) {
+              uint4 u;
+              u.x = pack16<BF16>(g[q], g[q + 1]);
+              u.y = pack16<BF16>(g[q + 2], g[q + 3]);
+              u.z = pack16<BF16>(g[q + 4], g[q + 5]);
+              u.w = pack16<BF16>(g[q + 6], g[q + 7]);
+              *reinterpret_cast<uint4*>(og + q) = u;
+            }
+            continue;
           }
           uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
           if (vec) {
@@ -301,10 +362,28 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 *reinterpret_cast<uint4*>(op + q) = u;
               }
             }
-          } else {
+          } else if (live) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
+            }
+          }
+          if (do_stats) {
+            // per-channel sum / sum of squares of the values as stored (rounded to 16 bit); rows outside
+            // the image and padding columns contribute zero.  All 32 lanes take part in the shuffles.
+            float sq[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float a = (live && q < nvalid) ? cvt16<BF16>((uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF)) : 0.f;
+              v[q] = a;
+              sq[q] = a * a;
+            }
+            warp_transpose_sum(v, lane);
+            warp_transpose_sum(sq, lane);
+            if (lane < ncols && n0 + lane < p.Cout) {
+              float* d = sacc + ((size_t)wq * p.Cout + n0 + lane) * 2;
+              d[0] += v[0];
+              d[1] += sq[0];
             }
           }
         }
@@ -318,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (do_stats && cur_img >= 0) flush_stats(cur_img);
   }
 
   tc_fence_before();
@@ -408,14 +488,23 @@ const char* igemm_finalize(IgemmParams* p) {
   if (total > 0x7fffffffLL) return "too many tiles";
   p->total_tiles = (int)total;
   const int stage_bytes = kABytes * p->MT + p->BN * 128;
-  int st = (kMaxSmem - 2048) / stage_bytes;
+  const int stats_bytes = p->stats ? 4 * p->Cout * 2 * (int)sizeof(float) : 0;
+  if (p->stats && (p->Cout > 512 || (p->flags & (IG_OUT_F32_NCHW | IG_GEGLU)))) return "stats need Cout <= 512, 16-bit NHWC";
+  int st = (kMaxSmem - 2048 - stats_bytes) / stage_bytes;
   if (st > 8) st = 8;
   if (st < 2) return "tile too large for shared memory";
   p->stages = st;
   return nullptr;
 }
 
-cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
+static cudaError_t igemm_init();
+
+int igemm_grid(const IgemmParams& p) {
+  if (igemm_init() != cudaSuccess) return 0;
+  return p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+}
+
+static cudaError_t igemm_init() {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -427,7 +516,14 @@ cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
+  return cudaSuccess;
+}
+
+cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
+  cudaError_t ie = igemm_init();
+  if (ie != cudaSuccess) return ie;
   if (p.total_tiles <= 0) return cudaSuccess;
+  if (p.stats && p.stats_slots < (p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms)) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   // always request the maximum so exactly one CTA (512 TMEM columns) is resident per SM
   const size_t smem = kMaxSmem;

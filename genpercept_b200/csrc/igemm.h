@@ -33,6 +33,8 @@ enum IgemmFlags : int {
   IG_OUT_F32_NCHW = 2,    // write fp32 planar [Z1, Cout, outH, outW] instead of 16-bit NHWC
   IG_AFFINE_CLAMP01 = 4,  // v = clamp((v + 1) / 2, 0, 1)   (genpercept_pipeline.py:470-472)
   IG_BF16 = 8,            // operands / 16-bit outputs are bf16 instead of fp16
+  IG_GEGLU = 16,          // columns come in chunks of 32 = [16 values | 16 gates]: out = value * gelu_erf(gate),
+                          // 16 outputs per chunk at column n/2 (ff.net.0 of BasicTransformerBlock)
 };
 
 struct IgemmParams {
@@ -63,7 +65,16 @@ struct IgemmParams {
   int flags;
   int stages;
   int total_tiles;
+  // Optional GroupNorm statistics of the (rounded) output, produced by the epilogue: per image and
+  // per CTA slot, per-channel sum / sum of squares, fp32, fixed summation order (deterministic):
+  //   stats[((image * stats_slots + blockIdx.x) * Cout + c) * 2 + {0, 1}]
+  // Pre-zeroed by the caller (CTAs that see no tile of an image do not write its slot).
+  float* stats;
+  int stats_slots;               // >= gridDim.x (igemm_grid())
+  int stats_hw;                  // tokens mode (Z1 == 1, gridH == 1): pixels per image; else 0
 };
+
+int igemm_grid(const IgemmParams& p);   // CTAs that igemm_launch will use for p (after igemm_finalize)
 
 // host helpers ----------------------------------------------------------------------------------
 // Encode a 4-D NHWC view (C, W, H, N) with element strides (sW, sH, sN) and box (64, TW, TH, 1).

@@ -136,7 +136,7 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int N, int Ctot, int groups, float inv_count,
                                    float eps, float* __restrict__ ss) {
   const int lane = threadIdx.x & 31;
@@ -144,19 +144,29 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   if (wid >= N * groups) return;
   const int n = wid / groups, g = wid % groups;
   const int cpg = Ctot / groups;
-  const int entries = cpg * chunks;
+  const int glo = g * cpg, ghi = glo + cpg;
   float s = 0.f, q = 0.f;
-  for (int i = lane; i < entries; i += 32) {
-    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
-    const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * chunks + ch) * Ctot + c) * 2);
-    s += v.x; q += v.y;
+  int cbase = 0;
+  for (int si = 0; si < nsrc; ++si) {
+    const GnSrc src = si == 0 ? s0 : s1;
+    const int lo = max(glo, cbase), hi = min(ghi, cbase + src.C);   // this group's channels inside the source
+    const int w = hi - lo;
+    if (w > 0) {
+      const int entries = w * src.chunks;
+      for (int i = lane; i < entries; i += 32) {
+        const int ch = i / w, c = lo - cbase + (i - ch * w);
+        const float2 v = *reinterpret_cast<const float2*>(src.partial + (((long long)n * src.chunks + ch) * src.C + c) * 2);
+        s += v.x; q += v.y;
+      }
+    }
+    cbase += src.C;
   }
   s = warp_sum(s); q = warp_sum(q);
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
   for (int i = lane; i < cpg; i += 32) {
-    const int c = g * cpg + i;
+    const int c = glo + i;
     const float sc = rstd * gamma[c];
     ss[((long long)n * Ctot + c) * 2] = sc;
     ss[((long long)n * Ctot + c) * 2 + 1] = beta[c] - mean * sc;
@@ -549,11 +559,13 @@ cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, 
   return cudaGetLastError();
 }
 
-cudaError_t gn_finalize(const float* partial, int chunks, const float* gamma, const float* beta, int N, int Ctot,
+cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const float* beta, int N, int Ctot,
                         int groups, long long HW, float eps, float* ss, cudaStream_t s) {
+  if (nsrc < 1 || nsrc > 2) return cudaErrorInvalidValue;
   const int warps = N * groups;
   const float inv_count = 1.0f / ((float)HW * (float)(Ctot / groups));
-  gn_finalize_kernel<<<(warps + 7) / 8, 256, 0, s>>>(partial, chunks, gamma, beta, N, Ctot, groups, inv_count, eps, ss);
+  gn_finalize_kernel<<<(warps + 7) / 8, 256, 0, s>>>(srcs[0], nsrc > 1 ? srcs[1] : srcs[0], nsrc, gamma, beta, N, Ctot,
+                                                       groups, inv_count, eps, ss);
   return cudaGetLastError();
 }
 

@@ -33,7 +33,10 @@ cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s);
 int gn_chunks(int N, long long HW);
 cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, int chunks, int Ctot, int coff,
                      bool bf16, cudaStream_t s);
-cudaError_t gn_finalize(const float* partial, int chunks, const float* gamma, const float* beta, int N, int Ctot,
+// one source of a (possibly concatenated) normalisation: partial sums [N][chunks][C][2]; the partials
+// come either from gn_stats or from the producing implicit-GEMM's epilogue (IgemmParams::stats).
+struct GnSrc { const float* partial; int chunks; int C; };
+cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const float* beta, int N, int Ctot,
                         int groups, long long HW, float eps, float* scale_shift /*[N][Ctot][2]*/, cudaStream_t s);
 cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* scale_shift, int Ctot,
                      int coff, void* y, int y_cstride, bool silu, bool bf16, cudaStream_t s);

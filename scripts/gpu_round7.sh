@@ -1,0 +1,5 @@
+#!/bin/bash
+bash scripts/gpu_quick.sh
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fattn_kernel -c 2 -f -o gpurun_out/prof_fattn \
+  python scripts/prof_attn.py > gpurun_out/prof_attn.log 2>&1
+echo "ncu fattn exit $?"; tail -n 3 gpurun_out/prof_attn.log
