@@ -154,7 +154,9 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const long long work_px = tokens_mode ? (long long)N * H * W
                                         : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
   const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
-  bool emit_stats = a.want_stats && !a.out_f32 && !(a.flags & IG_GEGLU) && Cout == a.out.C && Cout <= 512;
+  const bool staged = !a.out_f32 && !(a.flags & IG_GEGLU) && Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0 &&
+                      std::getenv("GP_DIRECT_EPILOGUE") == nullptr;
+  bool emit_stats = a.want_stats && staged && Cout <= 512;
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
   size_t stats_off = 0;
   const size_t stats_bytes = (size_t)N * num_sms * Cout * 2 * sizeof(float);
@@ -266,6 +268,27 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   }
   check_cuda(make_tmap_b(&p.tmB, a.w->w, a.w->ktot, a.w->rows, a.w->nz, a.w->ktot, (long long)a.w->rows * a.w->ktot,
                          p.BN, bf16_), name + ": tmap B");
+  if (staged) {   // output tensor maps for the TMA-store epilogue (one per parity class)
+    p.tma_store = 1;
+    const int bw = p.TW < 32 ? p.TW : 32, bh = 32 / bw;
+    if (tokens) {
+      const long long ntok = (long long)N * H * W;
+      check_cuda(make_tmap_a(&p.tmOut[0], ptr(a.out), out_c, (int)ntok, 1, 1, out_c, ntok * out_c, ntok * out_c, bw, bh, bf16_),
+                 name + ": tmap out");
+      for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
+    } else if (a.mode == 3) {
+      for (int c = 0; c < 4; ++c) {
+        const int py = c >> 1, px = c & 1;
+        const uint8_t* ob = reinterpret_cast<const uint8_t*>(ptr(a.out)) + ((long long)py * Wo + px) * out_c * 2;
+        check_cuda(make_tmap_a(&p.tmOut[c], ob, out_c, W, H, N, 2LL * out_c, 2LL * Wo * out_c, (long long)Ho * Wo * out_c, bw, bh,
+                               bf16_), name + ": tmap out");
+      }
+    } else {
+      check_cuda(make_tmap_a(&p.tmOut[0], ptr(a.out), out_c, Wo, Ho, N, out_c, (long long)Wo * out_c, (long long)Ho * Wo * out_c,
+                             bw, bh, bf16_), name + ": tmap out");
+      for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
+    }
+  }
   if (emit_stats) {
     p.stats = reinterpret_cast<float*>(raw_ptr(stats_off));
     p.stats_slots = num_sms;

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int a_bytes = kABytes * p.MT;
   const int stage_bytes = a_bytes + p.BN * 128;
   const int stages = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint8_t* stg_base = smem + stages * stage_bytes;                     // 4 x 4 KiB staging tiles (tma_store only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -205,6 +206,160 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  } else if (warp >= 4 && p.tma_store) {
+    // ===================================================================== epilogue, staged + TMA store
+    // TMEM -> registers (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile ->
+    // one TMA store per (warp, 64-channel group): full-line writes instead of 16-byte pieces at a
+    // 2C-byte stride, and image-edge clipping for free.  GroupNorm partial sums are read back
+    // column-wise from the staged tile (conflict-free), in a fixed order.
+    const int wq = warp - 4;
+    uint8_t* stg = stg_base + wq * 4096;
+    const uint32_t stg_addr = smem_u32(stg);
+    const uint32_t my_row = stg_addr + lane * 128;
+    const int sw = lane & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool relu = (p.flags & IG_RELU) != 0;
+    const bool do_stats = p.stats != nullptr;
+    const int etid = threadIdx.x - 128;
+    int cur_img = -1;
+    auto flush_stats = [&](int img) {
+      epi_sync();
+      float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
+      for (int i = etid; i < 2 * p.Cout; i += 128) {
+        const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
+        dst[i] = tot;
+        sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
+      }
+      epi_sync();
+    };
+    if (do_stats) {
+      for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
+      epi_sync();
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int cls = p.cls_from_z0 ? t.z0 : 0;
+      const int n_base = t.n_tile * p.BN;
+      bool waited = false;
+      if (do_stats) {
+        const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
+        if (img != cur_img) {
+          if (cur_img >= 0) flush_stats(cur_img);
+          cur_img = img;
+        }
+      }
+      for (int h = 0; h < p.MT; ++h) {
+        const int r0 = h * 128 + wq * 32;                       // first tile row of this warp
+        const int row = r0 + lane;
+        const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
+        const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
+        const bool valid = gy < p.gridH && gx < p.gridW;
+        const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
+        const long long pix_off = t.z1 * p.out_z1 + (long long)oy * p.out_row_stride + (long long)ox * p.out_pix_stride;
+        const int sx = t.tx * p.TW + (r0 & (p.TW - 1)), sy = t.ty * p.TH + (r0 >> p.tw_shift);   // store box origin
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
+        for (int c0 = 0; c0 < p.BN; c0 += 64) {
+          const int n0 = n_base + c0;
+          if (n0 >= p.Cout) break;
+          if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
+          __syncwarp();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int ns = n0 + sub * 32;
+            const long long off = pix_off + ns;
+            float bz[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) bz[q] = 0.f;
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
+                bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
+              }
+            }
+            uint4 r1[4], r2[4];
+            const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
+            if (has1) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) r1[q] = rp[q];
+            }
+            if (has2) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) r2[q] = rp[q];
+            }
+            if (!waited) {
+              mbar_wait(&tfull_bar[acc], acc_phase, 4);
+              tc_fence_after();
+              waited = true;
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0 + sub * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
+            if (has1) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r1[q]);
+            }
+            if (has2) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r2[q]);
+            }
+            if (relu) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
+            if (!valid) {      // rows outside the image are clipped by the TMA store; zero them for the statistics
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t a = my_row + (((sub * 4 + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16<BF16>(v[8 * i], v[8 * i + 1])),
+                           "r"(pack16<BF16>(v[8 * i + 2], v[8 * i + 3])), "r"(pack16<BF16>(v[8 * i + 4], v[8 * i + 5])),
+                           "r"(pack16<BF16>(v[8 * i + 6], v[8 * i + 7]))
+                           : "memory");
+            }
+          }
+          fence_proxy_async_shared();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmOut[cls], stg_addr, n0, sx, sy, t.z1);
+            tma_store_commit();
+          }
+          if (do_stats) {
+            // lane l owns channels n0 + 2l, n0 + 2l + 1: one 32-bit word per staged row
+            const uint32_t col = stg_addr + (lane & 3) * 4;
+            const int chunk = lane >> 2;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(col + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+              const float a = cvt16<BF16>((uint16_t)(w & 0xFFFF)), b = cvt16<BF16>((uint16_t)(w >> 16));
+              s0 += a; q0 += a * a; s1 += b; q1 += b * b;
+            }
+            float* d = sacc + ((size_t)wq * p.Cout + n0 + 2 * lane) * 2;
+            d[0] += s0; d[1] += q0; d[2] += s1; d[3] += q1;
+          }
+        }
+      }
+      if (!waited) {
+        mbar_wait(&tfull_bar[acc], acc_phase, 4);
+        tc_fence_after();
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_read0();
+    if (do_stats && cur_img >= 0) flush_stats(cur_img);
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int wq = warp - 4;                 // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
@@ -214,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const bool relu = (p.flags & IG_RELU) != 0;
     const bool aff = (p.flags & IG_AFFINE_CLAMP01) != 0;
     const bool geglu = (p.flags & IG_GEGLU) != 0;
-    const bool do_stats = p.stats != nullptr;
+    const bool do_stats = false;               // statistics are produced by the staged (TMA store) epilogue only
     const int etid = threadIdx.x - 128;        // 0..127 among the epilogue threads
     int cur_img = -1;
     // sum the four warp-private accumulators in a fixed order, publish this CTA's slot, reset
@@ -296,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           uint32_t r[32];
           if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
           tmem_ld_wait();
-          if (!live && !do_stats) continue;
+          if (!live) continue;
           float v[32];
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
@@ -366,24 +521,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
-            }
-          }
-          if (do_stats) {
-            // per-channel sum / sum of squares of the values as stored (rounded to 16 bit); rows outside
-            // the image and padding columns contribute zero.  All 32 lanes take part in the shuffles.
-            float sq[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float a = (live && q < nvalid) ? cvt16<BF16>((uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF)) : 0.f;
-              v[q] = a;
-              sq[q] = a * a;
-            }
-            warp_transpose_sum(v, lane);
-            warp_transpose_sum(sq, lane);
-            if (lane < ncols && n0 + lane < p.Cout) {
-              float* d = sacc + ((size_t)wq * p.Cout + n0 + lane) * 2;
-              d[0] += v[0];
-              d[1] += sq[0];
             }
           }
         }
@@ -489,8 +626,10 @@ const char* igemm_finalize(IgemmParams* p) {
   p->total_tiles = (int)total;
   const int stage_bytes = kABytes * p->MT + p->BN * 128;
   const int stats_bytes = p->stats ? 4 * p->Cout * 2 * (int)sizeof(float) : 0;
-  if (p->stats && (p->Cout > 512 || (p->flags & (IG_OUT_F32_NCHW | IG_GEGLU)))) return "stats need Cout <= 512, 16-bit NHWC";
-  int st = (kMaxSmem - 2048 - stats_bytes) / stage_bytes;
+  if (p->tma_store && ((p->Cout % 64) || (p->BN % 64) || (p->flags & (IG_OUT_F32_NCHW | IG_GEGLU)) || p->out_z0 != 0))
+    return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
+  if (p->stats && (!p->tma_store || p->Cout > 512)) return "statistics need the staged epilogue and Cout <= 512";
+  int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0)) / stage_bytes;
   if (st > 8) st = 8;
   if (st < 2) return "tile too large for shared memory";
   p->stages = st;

@@ -72,6 +72,11 @@ struct IgemmParams {
   float* stats;
   int stats_slots;               // >= gridDim.x (igemm_grid())
   int stats_hw;                  // tokens mode (Z1 == 1, gridH == 1): pixels per image; else 0
+  // Staged epilogue: each epilogue warp writes its 32 rows x 64 channels (16-bit) into a swizzled
+  // shared-memory tile and issues one TMA store (full 128-byte lines, image-edge clipping by the
+  // tensor map).  Needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output.  One map per class.
+  int tma_store;
+  CUtensorMap tmOut[kMaxClasses];   // (C, W, H, N) views of the output, box (64, min(TW,32), 32/min(TW,32), 1)
 };
 
 int igemm_grid(const IgemmParams& p);   // CTAs that igemm_launch will use for p (after igemm_finalize)
