@@ -289,6 +289,14 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
       for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
     }
   }
+  // patch-resident main loop for the wide-image, narrow-N 3x3 layers
+  if (staged && a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && p.MT == 2 && p.TW == 128 && p.TH == 2 &&
+      (W % 128) == 0 && (H % 2) == 0 && std::getenv("GP_NO_PATCH") == nullptr) {
+    p.patch = 1;
+    p.kc_count = ceil_div(s0.C, 64);
+    check_cuda(make_tmap_a(&p.tmPatch, ptr(s0), s0.C, W, H, N, s0.C, (long long)W * s0.C, (long long)H * W * s0.C,
+                           p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch");
+  }
   if (emit_stats) {
     p.stats = reinterpret_cast<float*>(raw_ptr(stats_off));
     p.stats_slots = num_sms;

@@ -92,6 +92,167 @@ __device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// Staged epilogue (shared by the tap-streaming and the patch-resident main loops): TMEM -> registers
+// (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile -> one TMA store per
+// (warp, 64-channel group), plus the GroupNorm partial sums read back column-wise from the tile.
+template <bool BF16>
+__device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, uint64_t* tfull_bar,
+                                                uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane) {
+  // ===================================================================== epilogue, staged + TMA store
+  // TMEM -> registers (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile ->
+  // one TMA store per (warp, 64-channel group): full-line writes instead of 16-byte pieces at a
+  // 2C-byte stride, and image-edge clipping for free.  GroupNorm partial sums are read back
+  // column-wise from the staged tile (conflict-free), in a fixed order.
+  const int wq = warp - 4;
+  uint8_t* stg = stg_base + wq * 4096;
+  const uint32_t stg_addr = smem_u32(stg);
+  const uint32_t my_row = stg_addr + lane * 128;
+  const int sw = lane & 7;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const bool relu = (p.flags & IG_RELU) != 0;
+  const bool do_stats = p.stats != nullptr;
+  const int etid = threadIdx.x - 128;
+  int cur_img = -1;
+  auto flush_stats = [&](int img) {
+    epi_sync();
+    float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
+    for (int i = etid; i < 2 * p.Cout; i += 128) {
+      const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
+      dst[i] = tot;
+      sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
+    }
+    epi_sync();
+  };
+  if (do_stats) {
+    for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
+    epi_sync();
+  }
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    const int cls = p.cls_from_z0 ? t.z0 : 0;
+    const int n_base = t.n_tile * p.BN;
+    bool waited = false;
+    if (do_stats) {
+      const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
+      if (img != cur_img) {
+        if (cur_img >= 0) flush_stats(cur_img);
+        cur_img = img;
+      }
+    }
+    for (int h = 0; h < p.MT; ++h) {
+      const int r0 = h * 128 + wq * 32;                       // first tile row of this warp
+      const int row = r0 + lane;
+      const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
+      const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
+      const bool valid = gy < p.gridH && gx < p.gridW;
+      const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
+      const long long pix_off = t.z1 * p.out_z1 + (long long)oy * p.out_row_stride + (long long)ox * p.out_pix_stride;
+      const int sx = t.tx * p.TW + (r0 & (p.TW - 1)), sy = t.ty * p.TH + (r0 >> p.tw_shift);   // store box origin
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
+      for (int c0 = 0; c0 < p.BN; c0 += 64) {
+        const int n0 = n_base + c0;
+        if (n0 >= p.Cout) break;
+        if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
+        __syncwarp();
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int ns = n0 + sub * 32;
+          const long long off = pix_off + ns;
+          float bz[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) bz[q] = 0.f;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
+              bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
+            }
+          }
+          uint4 r1[4], r2[4];
+          const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
+          if (has1) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r1[q] = rp[q];
+          }
+          if (has2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r2[q] = rp[q];
+          }
+          if (!waited) {
+            mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0 + sub * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
+          if (has1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r1[q]);
+          }
+          if (has2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r2[q]);
+          }
+          if (relu) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          if (!valid) {      // rows outside the image are clipped by the TMA store; zero them for the statistics
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = my_row + (((sub * 4 + i) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16<BF16>(v[8 * i], v[8 * i + 1])),
+                         "r"(pack16<BF16>(v[8 * i + 2], v[8 * i + 3])), "r"(pack16<BF16>(v[8 * i + 4], v[8 * i + 5])),
+                         "r"(pack16<BF16>(v[8 * i + 6], v[8 * i + 7]))
+                         : "memory");
+          }
+        }
+        fence_proxy_async_shared();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.tmOut[cls], stg_addr, n0, sx, sy, t.z1);
+          tma_store_commit();
+        }
+        if (do_stats) {
+          // lane l owns channels n0 + 2l, n0 + 2l + 1: one 32-bit word per staged row
+          const uint32_t col = stg_addr + (lane & 3) * 4;
+          const int chunk = lane >> 2;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(col + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+            const float a = cvt16<BF16>((uint16_t)(w & 0xFFFF)), b = cvt16<BF16>((uint16_t)(w >> 16));
+            s0 += a; q0 += a * a; s1 += b; q1 += b * b;
+          }
+          float* d = sacc + ((size_t)wq * p.Cout + n0 + 2 * lane) * 2;
+          d[0] += s0; d[1] += q0; d[2] += s1; d[3] += q1;
+        }
+      }
+    }
+    if (!waited) {
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+    }
+    tc_fence_before();
+    mbar_arrive(&tempty_bar[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (lane == 0) tma_store_wait_read0();
+  if (do_stats && cur_img >= 0) flush_stats(cur_img);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -207,159 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4 && p.tma_store) {
-    // ===================================================================== epilogue, staged + TMA store
-    // TMEM -> registers (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile ->
-    // one TMA store per (warp, 64-channel group): full-line writes instead of 16-byte pieces at a
-    // 2C-byte stride, and image-edge clipping for free.  GroupNorm partial sums are read back
-    // column-wise from the staged tile (conflict-free), in a fixed order.
-    const int wq = warp - 4;
-    uint8_t* stg = stg_base + wq * 4096;
-    const uint32_t stg_addr = smem_u32(stg);
-    const uint32_t my_row = stg_addr + lane * 128;
-    const int sw = lane & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const bool relu = (p.flags & IG_RELU) != 0;
-    const bool do_stats = p.stats != nullptr;
-    const int etid = threadIdx.x - 128;
-    int cur_img = -1;
-    auto flush_stats = [&](int img) {
-      epi_sync();
-      float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
-      for (int i = etid; i < 2 * p.Cout; i += 128) {
-        const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
-        dst[i] = tot;
-        sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
-      }
-      epi_sync();
-    };
-    if (do_stats) {
-      for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
-      epi_sync();
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const int cls = p.cls_from_z0 ? t.z0 : 0;
-      const int n_base = t.n_tile * p.BN;
-      bool waited = false;
-      if (do_stats) {
-        const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
-        if (img != cur_img) {
-          if (cur_img >= 0) flush_stats(cur_img);
-          cur_img = img;
-        }
-      }
-      for (int h = 0; h < p.MT; ++h) {
-        const int r0 = h * 128 + wq * 32;                       // first tile row of this warp
-        const int row = r0 + lane;
-        const int ti = row >> p.tw_shift, tj = row & (p.TW - 1);
-        const int gy = t.ty * p.TH + ti, gx = t.tx * p.TW + tj;
-        const bool valid = gy < p.gridH && gx < p.gridW;
-        const int oy = gy * p.out_sy + p.cls_py[cls], ox = gx * p.out_sx + p.cls_px[cls];
-        const long long pix_off = t.z1 * p.out_z1 + (long long)oy * p.out_row_stride + (long long)ox * p.out_pix_stride;
-        const int sx = t.tx * p.TW + (r0 & (p.TW - 1)), sy = t.ty * p.TH + (r0 >> p.tw_shift);   // store box origin
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
-        for (int c0 = 0; c0 < p.BN; c0 += 64) {
-          const int n0 = n_base + c0;
-          if (n0 >= p.Cout) break;
-          if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
-          __syncwarp();
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int ns = n0 + sub * 32;
-            const long long off = pix_off + ns;
-            float bz[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) bz[q] = 0.f;
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int q = 0; q < 32; q += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
-                bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
-              }
-            }
-            uint4 r1[4], r2[4];
-            const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
-            if (has1) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) r1[q] = rp[q];
-            }
-            if (has2) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) r2[q] = rp[q];
-            }
-            if (!waited) {
-              mbar_wait(&tfull_bar[acc], acc_phase, 4);
-              tc_fence_after();
-              waited = true;
-            }
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c0 + sub * 32, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + bz[q];
-            if (has1) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r1[q]);
-            }
-            if (has2) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r2[q]);
-            }
-            if (relu) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
-            }
-            if (!valid) {      // rows outside the image are clipped by the TMA store; zero them for the statistics
-#pragma unroll
-              for (int q = 0; q < 32; ++q) v[q] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t a = my_row + (((sub * 4 + i) ^ sw) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16<BF16>(v[8 * i], v[8 * i + 1])),
-                           "r"(pack16<BF16>(v[8 * i + 2], v[8 * i + 3])), "r"(pack16<BF16>(v[8 * i + 4], v[8 * i + 5])),
-                           "r"(pack16<BF16>(v[8 * i + 6], v[8 * i + 7]))
-                           : "memory");
-            }
-          }
-          fence_proxy_async_shared();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&p.tmOut[cls], stg_addr, n0, sx, sy, t.z1);
-            tma_store_commit();
-          }
-          if (do_stats) {
-            // lane l owns channels n0 + 2l, n0 + 2l + 1: one 32-bit word per staged row
-            const uint32_t col = stg_addr + (lane & 3) * 4;
-            const int chunk = lane >> 2;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(col + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
-              const float a = cvt16<BF16>((uint16_t)(w & 0xFFFF)), b = cvt16<BF16>((uint16_t)(w >> 16));
-              s0 += a; q0 += a * a; s1 += b; q1 += b * b;
-            }
-            float* d = sacc + ((size_t)wq * p.Cout + n0 + 2 * lane) * 2;
-            d[0] += s0; d[1] += q0; d[2] += s1; d[3] += q1;
-          }
-        }
-      }
-      if (!waited) {
-        mbar_wait(&tfull_bar[acc], acc_phase, 4);
-        tc_fence_after();
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (lane == 0) tma_store_wait_read0();
-    if (do_stats && cur_img >= 0) flush_stats(cur_img);
+    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int wq = warp - 4;                 // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
@@ -545,6 +554,132 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Patch-resident main loop (see IgemmParams::patch).  Same TMEM / epilogue protocol as igemm_kernel;
+// only the operand staging differs:
+//   shared memory = [2 halo-patch slots][B ring of `stages` weight tiles][staging tiles][barriers]
+//   warp 0 lane 0 : one TMA box (64 ch x 130 px x 4 rows) per K chunk into a patch slot
+//   warp 3 lane 0 : one weight box per (K chunk, tap) into the B ring
+//   warp 1 lane 0 : per K chunk, per tap, per image row h: 4 tcgen05.mma whose A descriptor starts
+//                   ((h + dy + 1) * 130 + dx + 1) rows into the patch (absolute-address swizzle makes
+//                   any 128-byte row a valid SWIZZLE_128B start: scripts/exp_baseoffset.cu)
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.BN * 128;
+  const int stages = p.stages;                       // B ring depth
+  uint8_t* sB = smem + 2 * p.a_slot_bytes;
+  uint8_t* stg_base = sB + stages * b_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + 4 * 4096);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + stages;
+  uint64_t* tfull_bar = b_empty + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sacc = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pw = p.TW + 2;                           // patch width in pixels
+  const uint32_t patch_bytes = (uint32_t)(pw * (p.TH + 2) * 128);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmPatch);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================================== patch producer
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int x0 = t.tx * p.TW - 1, y0 = t.ty * p.TH - 1;
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        mbar_wait(&a_empty[slot], phase ^ 1, 1);
+        mbar_expect_tx(&a_full[slot], patch_bytes);
+        tma_load_4d(smem + slot * p.a_slot_bytes, &p.tmPatch, &a_full[slot], kc * kBK, x0, y0, t.z1);
+        if (++slot == 2) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================================================================== weight producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int b_row = t.n_tile * p.BN;
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[stage], phase ^ 1, 5);
+          mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+          tma_load_3d(sB + stage * b_bytes, &p.tmB, &b_full[stage], (tap * p.kc_count + kc) * kBK, b_row, 0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
+    int slot = 0, stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((p.seg[0][tap].dy + 1) * pw + p.seg[0][tap].dx + 1) * 128;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        mbar_wait(&a_full[slot], a_phase, 3);
+        tc_fence_after();
+        const uint32_t patch = smem_u32(smem + slot * p.a_slot_bytes);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[stage], b_phase, 6);
+          tc_fence_after();
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * b_bytes));
+          for (int h = 0; h < p.TH; ++h) {
+            const uint64_t a_desc = make_sw128_kmajor_desc(patch + tap_off[tap] + h * pw * 128);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16(d_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) ? 1u : 0u);
+          }
+          umma_commit(&b_empty[stage]);
+          if (++stage == stages) { stage = 0; b_phase ^= 1; }
+        }
+        umma_commit(&a_empty[slot]);
+        if (++slot == 2) { slot = 0; a_phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -630,6 +765,12 @@ const char* igemm_finalize(IgemmParams* p) {
     return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
   if (p->stats && (!p->tma_store || p->Cout > 512)) return "statistics need the staged epilogue and Cout <= 512";
   int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0)) / stage_bytes;
+  if (p->patch) {
+    if (!p->tma_store || p->MT != 2 || p->TW != 128 || p->TH != 2 || p->Z0 != 1 || p->nseg[0] != 9 || p->n_tiles_n < 1)
+      return "patch mode needs the staged epilogue, TW = 128, MT = 2 and a single-source 3x3 tap table";
+    p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
+    st = (kMaxSmem - 2048 - stats_bytes - 4 * 4096 - 2 * p->a_slot_bytes) / (p->BN * 128);
+  }
   if (st > 8) st = 8;
   if (st < 2) return "tile too large for shared memory";
   p->stages = st;
@@ -650,6 +791,10 @@ static cudaError_t igemm_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(igemm_patch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(igemm_patch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -666,10 +811,16 @@ cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   // always request the maximum so exactly one CTA (512 TMEM columns) is resident per SM
   const size_t smem = kMaxSmem;
-  if (p.flags & IG_BF16)
+  if (p.patch) {
+    if (p.flags & IG_BF16)
+      igemm_patch_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    else
+      igemm_patch_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  } else if (p.flags & IG_BF16) {
     igemm_kernel<true><<<grid, kThreads, smem, stream>>>(p);
-  else
+  } else {
     igemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

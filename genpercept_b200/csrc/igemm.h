@@ -77,6 +77,15 @@ struct IgemmParams {
   // tensor map).  Needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output.  One map per class.
   int tma_store;
   CUtensorMap tmOut[kMaxClasses];   // (C, W, H, N) views of the output, box (64, min(TW,32), 32/min(TW,32), 1)
+  // Patch-resident main loop (3x3 stride-1, one source, TW = 128, MT = 2, staged epilogue): per
+  // 64-channel K chunk ONE (TH+2) x (TW+2) halo patch is loaded and all nine taps are fed from it by
+  // row-offset descriptors (tap (dy,dx) starts (h+dy+1)*(TW+2) + dx+1 rows into the patch), instead of
+  // nine shifted boxes.  Cuts the activation L2->SM traffic 9 -> 2.03 reads per element: the narrow-N
+  // (Cout = 128) layers are bound by exactly that traffic (~42 B/clk/SM of unique data).
+  int patch;
+  int kc_count;                  // 64-channel K chunks per tap (packed weights are tap-major, kc_count*64 wide per tap)
+  int a_slot_bytes;              // bytes reserved per patch slot (2 slots), multiple of 1024
+  CUtensorMap tmPatch;           // (C, W, H, N) view of the source, box (64, TW+2, TH+2, 1)
 };
 
 int igemm_grid(const IgemmParams& p);   // CTAs that igemm_launch will use for p (after igemm_finalize)

@@ -88,13 +88,19 @@ def test_igemm_linear_bias_residual_relu():
 @pytest.mark.parametrize("shape", [(1, 16, 16, 64, 64), (2, 32, 32, 128, 128), (1, 24, 24, 320, 320),
                                    (1, 12, 12, 1280, 256), (2, 96, 96, 128, 256), (1, 8, 8, 512, 512),
                                    (1, 4, 4, 64, 32), (1, 2, 2, 64, 16), (1, 1, 1, 128, 64), (1, 48, 48, 1920, 640),
-                                   (1, 128, 128, 128, 128), (1, 64, 64, 256, 8), (2, 32, 32, 8, 128), (1, 16, 16, 8, 320)])
+                                   (1, 128, 128, 128, 128), (1, 64, 64, 256, 8), (2, 32, 32, 8, 128), (1, 16, 16, 8, 320),
+                                   # wide images with narrow N: the patch-resident main loop (halo reuse)
+                                   (2, 256, 256, 128, 128), (1, 256, 256, 64, 64), (1, 256, 384, 256, 128)])
 def test_igemm_conv3x3(shape):
     _run_conv(*shape, 3, 0, direct=False)
 
 
 def test_igemm_conv3x3_residual():
     _run_conv(2, 32, 32, 256, 256, 3, 0, direct=False, residual=True)
+
+
+def test_igemm_conv3x3_patch_mode_residual_relu():
+    _run_conv(1, 256, 256, 128, 128, 3, 0, direct=False, residual=True, relu=True)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
