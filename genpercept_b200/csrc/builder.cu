@@ -154,9 +154,11 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const long long work_px = tokens_mode ? (long long)N * H * W
                                         : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
   const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
-  const bool staged = !a.out_f32 && !(a.flags & IG_GEGLU) && Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0 &&
-                      std::getenv("GP_DIRECT_EPILOGUE") == nullptr;
-  bool emit_stats = a.want_stats && staged && Cout <= 512;
+  const bool is_geglu = (a.flags & IG_GEGLU) != 0;
+  const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
+                      (is_geglu ? (Cout == 2 * a.out.C && (Cout % 128) == 0 && (bn_pre % 128) == 0)
+                                : (Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0));
+  bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512;
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
   size_t stats_off = 0;
   const size_t stats_bytes = (size_t)N * num_sms * Cout * 2 * sizeof(float);

@@ -111,6 +111,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   int acc = 0;
   uint32_t acc_phase = 0;
   const bool relu = (p.flags & IG_RELU) != 0;
+  const bool geglu = (p.flags & IG_GEGLU) != 0;
   const bool do_stats = p.stats != nullptr;
   const int etid = threadIdx.x - 128;
   int cur_img = -1;
@@ -153,6 +154,54 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
       for (int c0 = 0; c0 < p.BN; c0 += 64) {
         const int n0 = n_base + c0;
         if (n0 >= p.Cout) break;
+        if (geglu) {   // 128 GEMM columns = 4 x [16 values | 16 gates] -> 64 outputs = one staged 128-byte row
+          if (c0 & 64) continue;
+          if (lane == 0) tma_store_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) {
+            const int ns = n0 + sub * 32;
+            float bz[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) bz[q] = 0.f;
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
+                bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
+              }
+            }
+            if (!waited) {
+              mbar_wait(&tfull_bar[acc], acc_phase, 4);
+              tc_fence_after();
+              waited = true;
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0 + sub * 32, r);
+            tmem_ld_wait();
+            float g[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float a = __uint_as_float(r[q]) + bz[q], gt = __uint_as_float(r[16 + q]) + bz[16 + q];
+              g[q] = valid ? a * (0.5f * gt * (1.f + erff(gt * 0.70710678118654752f))) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t a = my_row + (((sub * 2 + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16<BF16>(g[8 * i], g[8 * i + 1])),
+                           "r"(pack16<BF16>(g[8 * i + 2], g[8 * i + 3])), "r"(pack16<BF16>(g[8 * i + 4], g[8 * i + 5])),
+                           "r"(pack16<BF16>(g[8 * i + 6], g[8 * i + 7]))
+                           : "memory");
+            }
+          }
+          fence_proxy_async_shared();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmOut[cls], stg_addr, n0 >> 1, sx, sy, t.z1);
+            tma_store_commit();
+          }
+          continue;
+        }
         if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
         __syncwarp();
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -761,9 +810,10 @@ const char* igemm_finalize(IgemmParams* p) {
   p->total_tiles = (int)total;
   const int stage_bytes = kABytes * p->MT + p->BN * 128;
   const int stats_bytes = p->stats ? 4 * p->Cout * 2 * (int)sizeof(float) : 0;
-  if (p->tma_store && ((p->Cout % 64) || (p->BN % 64) || (p->flags & (IG_OUT_F32_NCHW | IG_GEGLU)) || p->out_z0 != 0))
+  if (p->tma_store && ((p->Cout % 64) || (p->BN % 64) || (p->flags & IG_OUT_F32_NCHW) || p->out_z0 != 0))
     return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
-  if (p->stats && (!p->tma_store || p->Cout > 512)) return "statistics need the staged epilogue and Cout <= 512";
+  if (p->tma_store && (p->flags & IG_GEGLU) && ((p->Cout % 128) || (p->BN % 128))) return "staged GEGLU needs Cout, BN % 128 == 0";
+  if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
   int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0)) / stage_bytes;
   if (p->patch) {
     if (!p->tma_store || p->MT != 2 || p->TW != 128 || p->TH != 2 || p->Z0 != 1 || p->nseg[0] != 9 || p->n_tiles_n < 1)
