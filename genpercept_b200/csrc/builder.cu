@@ -156,7 +156,8 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
-                      (is_geglu ? (Cout == 2 * a.out.C && (Cout % 128) == 0 && (bn_pre % 128) == 0)
+                      (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr &&   // measured slower than the direct GEGLU stores (r1g)
+                                   Cout == 2 * a.out.C && (Cout % 128) == 0 && (bn_pre % 128) == 0)
                                 : (Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0));
   bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512;
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
@@ -188,7 +189,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     p.MT = (p.BN <= 128 && ntok >= 256 * 148) ? 2 : 1;
     p.TW = 128 * p.MT; p.TH = 1; p.tw_shift = p.MT == 2 ? 8 : 7;
     p.nseg[0] = 1;
-    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(s0.C, 64)};
+    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(s0.C, 64)};
     p.outW = (int)ntok; p.outH = 1;
     p.out_pix_stride = out_c; p.out_row_stride = 0;
     check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.C, ntok * s0.C, ntok * s0.C, p.TW, 1, bf16_),
@@ -236,9 +237,9 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
       for (int r = 0; r < a.ks; ++r)
         for (int s = 0; s < a.ks; ++s)
           for (size_t i = 0; i < a.srcs.size(); ++i)
-            p.seg[0][ns++] = IgemmSeg{(int8_t)i, (int8_t)(r - half), (int8_t)(s - half), (uint8_t)ceil_div(a.srcs[i].C, 64)};
+            p.seg[0][ns++] = IgemmSeg{(int8_t)i, (int8_t)(r - half), (int8_t)(s - half), (uint16_t)ceil_div(a.srcs[i].C, 64)};
       for (size_t j = 0; j < a.sc.size(); ++j)
-        p.seg[0][ns++] = IgemmSeg{(int8_t)(a.srcs.size() + j), 0, 0, (uint8_t)ceil_div(a.sc[j].C, 64)};
+        p.seg[0][ns++] = IgemmSeg{(int8_t)(a.srcs.size() + j), 0, 0, (uint16_t)ceil_div(a.sc[j].C, 64)};
       GP_REQUIRE(ns <= kMaxSegs, name + ": too many K segments");
       p.nseg[0] = ns;
     } else if (a.mode == 1 || a.mode == 2) {
@@ -249,7 +250,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
           const int ty = r - pad, tx = s - pad;
           const int hp = ((ty % 2) + 2) % 2, wp = ((tx % 2) + 2) % 2;
           p.seg[0][ns++] = IgemmSeg{(int8_t)(hp * 2 + wp), (int8_t)((ty - hp) / 2), (int8_t)((tx - wp) / 2),
-                                    (uint8_t)ceil_div(s0.C, 64)};
+                                    (uint16_t)ceil_div(s0.C, 64)};
         }
       p.nseg[0] = ns;
     } else {
@@ -263,7 +264,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
         int ns = 0;
         for (int aa = 0; aa < 2; ++aa)
           for (int bb = 0; bb < 2; ++bb)
-            p.seg[c][ns++] = IgemmSeg{0, (int8_t)(py - 1 + aa), (int8_t)(px - 1 + bb), (uint8_t)ceil_div(s0.C, 64)};
+            p.seg[c][ns++] = IgemmSeg{0, (int8_t)(py - 1 + aa), (int8_t)(px - 1 + bb), (uint16_t)ceil_div(s0.C, 64)};
         p.nseg[c] = ns;
       }
     }
@@ -360,7 +361,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       p.a_n_z1 = 1; p.a_k_z0 = d;
       p.b_z_z1 = 1; p.b_k_z0 = d;
       p.nseg[0] = 1;
-      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(d, 64)};
+      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(d, 64)};
       p.out = S; p.outW = T; p.outH = 1;
       p.out_pix_stride = Tp; p.out_row_stride = 0;
       p.out_z1 = (long long)heads * T * Tp; p.out_z0 = (long long)T * Tp;
@@ -389,7 +390,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       p.a_n_z1 = heads; p.a_n_z0 = 1;
       p.b_z_z1 = 1; p.b_row_z0 = d;
       p.nseg[0] = 1;
-      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)ceil_div(T, 64)};
+      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(T, 64)};
       p.out = ptr(out); p.outW = T; p.outH = 1;
       p.out_pix_stride = C; p.out_row_stride = 0;
       p.out_z1 = (long long)T * C; p.out_z0 = d;
@@ -429,7 +430,7 @@ void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk
     p.Z1 = B; p.Z0 = 1;
     p.b_z_z1 = 1;
     p.nseg[0] = 1;
-    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)(wv.ktot / 64)};
+    p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)(wv.ktot / 64)};
     p.out = raw_ptr(vt_off); p.outW = C; p.outH = 1;
     p.out_pix_stride = Tp; p.out_row_stride = 0;
     p.out_z1 = (long long)C * Tp;

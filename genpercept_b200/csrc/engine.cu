@@ -1313,7 +1313,7 @@ gp_status gp_attention(int dtype, const void* q, const void* k, const void* v, i
       p.gridW = C; p.gridH = 1; p.TW = 128; p.TH = 1; p.tw_shift = 7;
       p.Z1 = B; p.Z0 = 1; p.b_z_z1 = 1;
       p.nseg[0] = 1;
-      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint8_t)(wv.ktot / 64)};
+      p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)(wv.ktot / 64)};
       p.out = vT; p.outW = C; p.outH = 1; p.out_pix_stride = Tp; p.out_z1 = (long long)C * Tp;
       p.out_sy = p.out_sx = 1;
       p.Cout = T;

@@ -185,6 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     const uint32_t prow = smem_u32(sP + t * kPBytes) + row * 128;
     const int sw = row & 7;
     const uint32_t ts = tmem_base + lane_off + t * 128;
+    // Ping-pong: the exp2-heavy pass 2 of the two tiles is forced to alternate (token passed through
+    // named barriers 2 / 3), so one tile's MUFU phase overlaps the other tile's wait / max / rescale
+    // phase instead of both tiles drifting into lock-step (r1f: 2535 cycles per tile-block vs the
+    // 1024-cycle MUFU bound).  Tile B hands the first token to tile A.
+    const bool pingpong = ntile == 2;
+    if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[t], j & 1, 15);
       tc_fence_after();
@@ -228,6 +234,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         for (int q = 0; q < 32; ++q) O[32 + q] = (O[32 + q] + __uint_as_float(rb[q])) * alpha;
       }
       l *= alpha;
+      if (pingpong) {
+        if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       // pass 2: probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
       const float mb = mx * c2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -254,6 +264,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
                        pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
       l += (l0 + l1) + (l2 + l3);
+      if (pingpong) {                             // hand the MUFU phase to the other tile
+        if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        else if (j + 1 < nblk) asm volatile("bar.arrive 2, 256;" ::: "memory");
+      }
       tc_fence_before();                          // S_t reads are complete before the MMA warp overwrites it
       fence_proxy_async_smem();                   // P_t visible to the tensor core (async proxy)
       mbar_arrive(&p_full[t]);

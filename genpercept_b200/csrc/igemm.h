@@ -25,7 +25,7 @@ constexpr int kBK = 64;       // channels per pipeline stage (= one 128-byte swi
 struct IgemmSeg {
   int8_t map;        // index into tmA
   int8_t dy, dx;     // tap offset in the map's pixel grid
-  uint8_t nchunks;   // ceil(C / 64)
+  uint16_t nchunks;  // ceil(C / 64)  (up to 256 for the P.V product over 16384 keys)
 };
 
 enum IgemmFlags : int {

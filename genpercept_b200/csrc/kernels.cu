@@ -340,73 +340,104 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
 }
 
 // ------------------------------------------------------------------------------ 2-token cross attention
-template <bool BF16>
+// y = x + c0 + sigmoid(LN(x).U + u0).M : one warp handles TOK tokens at once so every U / M / c0 vector
+// fetched from L1/L2 is reused TOK times (the single-token version re-read ~2*heads*C*4 bytes per token).
+template <bool BF16, int KV, int TOK>
 __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens, int C,
                               int heads, const float* __restrict__ U, const float* __restrict__ u0,
                               const float* __restrict__ M, const float* __restrict__ c0, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tok >= tokens) return;
+  const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
+  if (tok0 >= tokens) return;
   const int nvec = C / 8;
-  float f[kLnMaxVec][8];
-  float s = 0.f;
+  float f[TOK][KV][8];
+  float mean[TOK], rstd[TOK];
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int t = 0; t < TOK; ++t) {
+    const bool tv = tok0 + t < tokens;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec && tv) {
+        unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + (tok0 + t) * C + v * 8)), f[t][i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[t][i][e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[t][i][e];
+    }
+    mean[t] = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[t][i][e] - mean[t]; q += d * d; }
+      }
+    }
+    rstd[t] = rsqrtf(warp_sum(q) / C + eps);
+  }
+  float acc[TOK][KV][8];
+#pragma unroll
+  for (int i = 0; i < KV; ++i) {
     const int v = lane + 32 * i;
     if (v < nvec) {
-      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + tok * C + v * 8)), f[i]);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(c0 + v * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(c0 + v * 8 + 4));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += f[i][e];
-    }
-  }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    if (lane + 32 * i < nvec) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
-  float acc[kLnMaxVec][8];
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[i][e] = f[i][e] + __ldg(c0 + v * 8 + e);
+      for (int t = 0; t < TOK; ++t) {
+        acc[t][i][0] = f[t][i][0] + a.x; acc[t][i][1] = f[t][i][1] + a.y; acc[t][i][2] = f[t][i][2] + a.z; acc[t][i][3] = f[t][i][3] + a.w;
+        acc[t][i][4] = f[t][i][4] + b.x; acc[t][i][5] = f[t][i][5] + b.y; acc[t][i][6] = f[t][i][6] + b.z; acc[t][i][7] = f[t][i][7] + b.w;
+      }
     }
   }
   for (int h = 0; h < heads; ++h) {
-    float d = 0.f;
+    float d[TOK];
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int t = 0; t < TOK; ++t) d[t] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(U + (long long)h * C + v * 8));
         const float4 b = __ldg(reinterpret_cast<const float4*>(U + (long long)h * C + v * 8 + 4));
-        d += (f[i][0] - mean) * a.x + (f[i][1] - mean) * a.y + (f[i][2] - mean) * a.z + (f[i][3] - mean) * a.w +
-             (f[i][4] - mean) * b.x + (f[i][5] - mean) * b.y + (f[i][6] - mean) * b.z + (f[i][7] - mean) * b.w;
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) {
+          const float mt = mean[t];
+          d[t] += (f[t][i][0] - mt) * a.x + (f[t][i][1] - mt) * a.y + (f[t][i][2] - mt) * a.z + (f[t][i][3] - mt) * a.w +
+                  (f[t][i][4] - mt) * b.x + (f[t][i][5] - mt) * b.y + (f[t][i][6] - mt) * b.z + (f[t][i][7] - mt) * b.w;
+        }
       }
     }
-    d = warp_sum(d) * rstd + __ldg(u0 + h);
-    const float pr = 1.f / (1.f + __expf(-d));
+    float pr[TOK];
+    const float u0h = __ldg(u0 + h);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int t = 0; t < TOK; ++t) pr[t] = 1.f / (1.f + __expf(-(warp_sum(d[t]) * rstd[t] + u0h)));
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(M + (long long)h * C + v * 8));
         const float4 b = __ldg(reinterpret_cast<const float4*>(M + (long long)h * C + v * 8 + 4));
-        acc[i][0] += pr * a.x; acc[i][1] += pr * a.y; acc[i][2] += pr * a.z; acc[i][3] += pr * a.w;
-        acc[i][4] += pr * b.x; acc[i][5] += pr * b.y; acc[i][6] += pr * b.z; acc[i][7] += pr * b.w;
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) {
+          acc[t][i][0] += pr[t] * a.x; acc[t][i][1] += pr[t] * a.y; acc[t][i][2] += pr[t] * a.z; acc[t][i][3] += pr[t] * a.w;
+          acc[t][i][4] += pr[t] * b.x; acc[t][i][5] += pr[t] * b.y; acc[t][i][6] += pr[t] * b.z; acc[t][i][7] += pr[t] * b.w;
+        }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) *reinterpret_cast<uint4*>(y + tok * C + v * 8) = pack8<BF16>(acc[i]);
+  for (int t = 0; t < TOK; ++t) {
+    if (tok0 + t < tokens) {
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) *reinterpret_cast<uint4*>(y + (tok0 + t) * C + v * 8) = pack8<BF16>(acc[t][i]);
+      }
+    }
   }
 }
 
@@ -621,15 +652,30 @@ cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cu
   return cudaGetLastError();
 }
 
+template <bool BF, int KV, int TOK>
+static cudaError_t xattn2_launch(const void* x, void* y, long long tokens, int C, int heads, const float* U, const float* u0,
+                                 const float* M, const float* c0, float eps, cudaStream_t s) {
+  const int wpb = 4;
+  const long long per_block = (long long)wpb * TOK;
+  const long long blocks = (tokens + per_block - 1) / per_block;
+  xattn2_kernel<BF, KV, TOK><<<(unsigned)blocks, wpb * 32, 0, s>>>(reinterpret_cast<const uint16_t*>(x),
+                                                                    reinterpret_cast<uint16_t*>(y), tokens, C, heads, U, u0, M,
+                                                                    c0, eps);
+  return cudaGetLastError();
+}
+
 cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, const float* U, const float* u0,
                    const float* M, const float* c0, float eps, bool bf16, cudaStream_t s) {
   if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
-  const int tpb = 8;
-  const long long blocks = (tokens + tpb - 1) / tpb;
-  GP_DISPATCH_BF16(bf16, (xattn2_kernel<BF><<<(unsigned)blocks, tpb * 32, 0, s>>>(
-                             reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), tokens, C, heads, U,
-                             u0, M, c0, eps)));
-  return cudaGetLastError();
+  const int kv = (C / 8 + 31) / 32;
+  cudaError_t e = cudaSuccess;
+  if (kv <= 2)
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 2, 4>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+  else if (kv <= 3)
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 3, 2>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+  else
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 5, 1>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+  return e;
 }
 
 cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16, cudaStream_t s) {
