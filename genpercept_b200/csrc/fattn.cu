@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         if (done[t ^ 1] >= j + 1) umma_commit(&kv_empty[j % kStages]);   // both tiles have issued every use of block j
         progressed = true;
       }
-      if (!progressed && clock64() - t_start > 8000000000LL) {
+      if (!progressed && clock64() - t_start > 100000000000LL) {
         printf("[gp] fattn MMA watchdog: block %d done %d %d of %d\n", (int)blockIdx.x, done[0], done[1], nblk);
         __trap();
       }
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     // named barriers 2 / 3), so one tile's MUFU phase overlaps the other tile's wait / max / rescale
     // phase instead of both tiles drifting into lock-step (r1f: 2535 cycles per tile-block vs the
     // 1024-cycle MUFU bound).  Tile B hands the first token to tile A.
-    const bool pingpong = ntile == 2;
+    // (measured: the forced alternation is slower, 13.0 vs 11.9 ms per step, r1g; kept behind a switch)
+    const bool pingpong = false && ntile == 2;
     if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[t], j & 1, 15);

@@ -325,10 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 2);    // producer A + producer B
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.MT);  // one tcgen05.commit per MMA issuer
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tfull_bar[i], p.MT);
       mbar_init(&tempty_bar[i], 128);
     }
     fence_barrier_init();
@@ -381,10 +381,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
+  } else if ((warp == 1 || (warp == 2 && p.MT == 2)) && lane == 0) {
+    // ===================================================================== MMA issuer(s)
+    // With two accumulator tiles (MT = 2, BN <= 128) each tile gets its own issuing thread: a single
+    // thread cannot issue one 64-cycle 128x128x16 MMA every 64 cycles once descriptor arithmetic and
+    // barrier polls are added (ncu r1h: tensor pipe 57 % busy, issuer never blocked on a barrier).
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
-    const int mt = p.MT;
+    const int h_lo = warp - 1, h_hi = (p.MT == 2) ? warp : 1;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
         const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_bytes);
-        for (int h = 0; h < mt; ++h) {
+        for (int h = h_lo; h < h_hi; ++h) {
           const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + h * kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
@@ -598,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
+    __syncwarp();          // lane 0 may come from the MMA-issuer branch: reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -637,9 +641,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmPatch);
     tma_prefetch_desc(&p.tmB);
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }        // two MMA issuers
+    for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 2); mbar_init(&tempty_bar[i], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -678,9 +682,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
+  } else if ((warp == 1 || warp == 2) && lane == 0) {
+    // ===================================================================== MMA issuers (one per image row h)
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
+    const int h = warp - 1;
     int slot = 0, stage = 0;
     uint32_t a_phase = 0, b_phase = 0;
     int acc = 0;
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
           mbar_wait(&b_full[stage], b_phase, 6);
           tc_fence_after();
           const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * b_bytes));
-          for (int h = 0; h < p.TH; ++h) {
+          {
             const uint64_t a_desc = make_sw128_kmajor_desc(patch + tap_off[tap] + h * pw * 128);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
@@ -724,6 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
+    __syncwarp();          // lane 0 may come from the MMA-issuer branch: reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

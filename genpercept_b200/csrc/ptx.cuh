@@ -37,12 +37,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin with a watchdog: a protocol bug must become a trap (reported CUDA error), never a hang of
-// the GPU box.  ~4e9 cycles is >2 s at 1.9 GHz; no correct wait is anywhere near that long.
+// the GPU box.  1e11 cycles is ~1 minute: far beyond any correct wait, yet tolerant of ncu's
+// instrumented replay passes (a 2 s limit fired under `ncu --set full`).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > 100000000000LL) {
       printf("[gp] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
       __trap();
