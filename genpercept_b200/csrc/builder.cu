@@ -159,7 +159,12 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
                       (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr &&   // measured slower than the direct GEGLU stores (r1g)
                                    Cout == 2 * a.out.C && (Cout % 128) == 0 && (bn_pre % 128) == 0)
                                 : (Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0));
-  bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512;
+  // GP_STATS: 0 = never fuse the GroupNorm partial sums into conv epilogues, 1 = always (default), 2 = everywhere
+  // except the patch-resident layers (whose main loop runs at the tensor-pipe limit, so the epilogue is critical)
+  static const int stats_mode = std::getenv("GP_STATS") ? std::atoi(std::getenv("GP_STATS")) : 1;
+  const bool patch_eligible = a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && mt_pre == 2 && (W % 128) == 0 &&
+                              (H % 2) == 0 && std::getenv("GP_NO_PATCH") == nullptr;
+  bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512 && stats_mode != 0 && !(stats_mode == 2 && patch_eligible);
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
   size_t stats_off = 0;
   const size_t stats_bytes = (size_t)N * num_sms * Cout * 2 * sizeof(float);

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], ntile); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
     for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
     fence_barrier_init();
@@ -115,61 +115,44 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       tma_load_3d(sV + st * kVBytes, &p.tmV, &kv_full[st], j * 128, head * 64, b);
       tma_load_3d(sV + st * kVBytes + 8192, &p.tmV, &kv_full[st], j * 128 + 64, head * 64, b);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if ((warp == 1 || warp == 3) && lane == 0 && ((warp - 1) >> 1) < ntile) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile A, warp 3 -> tile B
+    // One issuing thread per tile: the 32-cycle 128x64x16 P.V instructions are issue-bound from a single
+    // thread, and a shared issuer made each tile wait behind the other's instruction stream.  The next
+    // score tile S_t,j+1 is issued before the P.V product of block j (the softmax warps idle until it lands).
+    const int t = (warp - 1) >> 1;
     const uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);
     const uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0);
-    auto mma_s = [&](int t, int j) {          // S_t = Q_t K_j^T ; caller guarantees kv_full(j) was observed
-      const int st = j % kStages;
-      const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ + t * kQBytes));
-      const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK + st * kKBytes));
+    const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ + t * kQBytes));
+    const uint32_t p_base = smem_u32(sP + t * kPBytes);
+    auto mma_s = [&](int j) {                 // S_t = Q_t K_j^T
+      const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK + (j % kStages) * kKBytes));
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_f16(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k ? 1u : 0u);
       umma_commit(&s_full[t]);
     };
-    auto mma_o = [&](int t, int j) {          // O_t[j&1] = P_t V_j
-      const int st = j % kStages;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint64_t a = make_sw128_kmajor_desc(smem_u32(sP + t * kPBytes + (kk >> 2) * 16384)) + 2 * (kk & 3);
-        const uint64_t bd = make_sw128_kmajor_desc(smem_u32(sV + st * kVBytes + (kk >> 2) * 8192)) + 2 * (kk & 3);
-        umma_f16(tmem_base + kOCol + t * 128 + (j & 1) * 64, a, bd, idesc_o, kk ? 1u : 0u);
-      }
-      umma_commit(&o_full[t * 2 + (j & 1)]);
-    };
     mbar_wait(q_full, 0, 12);
     mbar_wait(&kv_full[0], 0, 11);
     tc_fence_after();
-    for (int t = 0; t < ntile; ++t) mma_s(t, 0);
-    // Event loop over the two tiles: whichever tile has published P_t,j first is served first, and
-    // its NEXT score tile S_t,j+1 is issued before the P.V product of block j, because the softmax
-    // warps of tile t idle until S_t,j+1 lands (r1e: 26 % of their time with the in-order schedule).
-    int done[2] = {0, ntile == 2 ? 0 : nblk};
-    int kv_seen = 0;                               // highest K/V block whose kv_full has been observed
-    const long long t_start = clock64();
-    while (done[0] < nblk || done[1] < nblk) {
-      bool progressed = false;
-      for (int t = 0; t < ntile; ++t) {
-        const int j = done[t];
-        if (j >= nblk || !mbar_try_wait(&p_full[t], j & 1)) continue;
+    mma_s(0);
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % kStages;
+      if (j + 1 < nblk) {
+        mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1, 11);
         tc_fence_after();
-        if (j + 1 < nblk) {
-          if (kv_seen < j + 1) {
-            mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1, 11);
-            tc_fence_after();
-            kv_seen = j + 1;
-          }
-          mma_s(t, j + 1);
-        }
-        mma_o(t, j);
-        done[t] = j + 1;
-        if (done[t ^ 1] >= j + 1) umma_commit(&kv_empty[j % kStages]);   // both tiles have issued every use of block j
-        progressed = true;
       }
-      if (!progressed && clock64() - t_start > 100000000000LL) {
-        printf("[gp] fattn MMA watchdog: block %d done %d %d of %d\n", (int)blockIdx.x, done[0], done[1], nblk);
-        __trap();
+      mbar_wait(&p_full[t], j & 1, 13);       // P_t,j is in shared memory and S_t has been consumed
+      tc_fence_after();
+      if (j + 1 < nblk) mma_s(j + 1);
+      const uint32_t v_base = smem_u32(sV + st * kVBytes);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint64_t a = make_sw128_kmajor_desc(p_base + (kk >> 2) * 16384) + 2 * (kk & 3);
+        const uint64_t bd = make_sw128_kmajor_desc(v_base + (kk >> 2) * 8192) + 2 * (kk & 3);
+        umma_f16(tmem_base + kOCol + t * 128 + (j & 1) * 64, a, bd, idesc_o, kk ? 1u : 0u);
       }
+      umma_commit(&o_full[t * 2 + (j & 1)]);
+      umma_commit(&kv_empty[st]);             // this tile has issued every use of block j (barrier counts both tiles)
     }
   } else if (warp >= 4 && (warp - 4) / 4 < ntile) {
     // ------------------------------------------------------------------ softmax + output of tile t
