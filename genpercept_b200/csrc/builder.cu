@@ -345,6 +345,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
     p.T = T; p.heads = heads; p.B = B; p.q_tiles = ceil_div(T, 128);
     p.scale_log2e = 1.4426950408889634f;
     p.bf16 = bf16_ ? 1 : 0;
+    p.trace = fattn_get_trace();
     check_cuda(make_tmap_b(&p.tmQ, q, C, T, B, cs, (long long)T * cs, 128, bf16_), name + ": tmap Q");
     check_cuda(make_tmap_b(&p.tmK, k, C, T, B, cs, (long long)T * cs, 128, bf16_), name + ": tmap K");
     check_cuda(make_tmap_b(&p.tmV, vT, T, C, B, Tp, (long long)C * Tp, 64, bf16_), name + ": tmap Vt");

@@ -141,9 +141,13 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1, 11);
         tc_fence_after();
       }
+      const bool trm = p.trace != nullptr && blockIdx.x == 0 && t == 0 && j < 64;
+      if (trm) p.trace[512 + j * 4 + 0] = clock64();
       mbar_wait(&p_full[t], j & 1, 13);       // P_t,j is in shared memory and S_t has been consumed
       tc_fence_after();
+      if (trm) p.trace[512 + j * 4 + 1] = clock64();
       if (j + 1 < nblk) mma_s(j + 1);
+      if (trm) p.trace[512 + j * 4 + 2] = clock64();
       const uint32_t v_base = smem_u32(sV + st * kVBytes);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       }
       umma_commit(&o_full[t * 2 + (j & 1)]);
       umma_commit(&kv_empty[st]);             // this tile has issued every use of block j (barrier counts both tiles)
+      if (trm) p.trace[512 + j * 4 + 3] = clock64();
     }
   } else if (warp >= 4 && (warp - 4) / 4 < ntile) {
     // ------------------------------------------------------------------ softmax + output of tile t
@@ -175,9 +180,12 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     // (measured: the forced alternation is slower, 13.0 vs 11.9 ms per step, r1g; kept behind a switch)
     const bool pingpong = false && ntile == 2;
     if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && t == 0 && wq == 0 && lane == 0;
     for (int j = 0; j < nblk; ++j) {
+      if (tr && j < 64) p.trace[j * 8 + 0] = clock64();
       mbar_wait(&s_full[t], j & 1, 15);
       tc_fence_after();
+      if (tr && j < 64) p.trace[j * 8 + 1] = clock64();
       const int kvalid = min(128, T - j * 128);
       uint32_t ra[32], rb[32];
       // pass 1: row maximum (4 independent chains, TMEM loads one chunk ahead)
@@ -203,10 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float alpha = ex2((m - mx) * c2);
+      if (tr && j < 64) p.trace[j * 8 + 2] = clock64();
       tmem_ld_32x32(ts, ra);                       // first chunk of pass 2, in flight during the O update
       if (j > 0) {
         mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 16);
         tc_fence_after();
+        if (tr && j < 64) p.trace[j * 8 + 3] = clock64();
         const uint32_t to = tmem_base + lane_off + kOCol + t * 128 + ((j - 1) & 1) * 64;
         tmem_ld_32x32(to, rb);
         tmem_ld_wait();
@@ -218,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         for (int q = 0; q < 32; ++q) O[32 + q] = (O[32 + q] + __uint_as_float(rb[q])) * alpha;
       }
       l *= alpha;
+      if (tr && j < 64) p.trace[j * 8 + 4] = clock64();
       if (pingpong) {
         if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
         else asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -248,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
                        pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
       l += (l0 + l1) + (l2 + l3);
+      if (tr && j < 64) p.trace[j * 8 + 5] = clock64();
       if (pingpong) {                             // hand the MUFU phase to the other tile
         if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
         else if (j + 1 < nblk) asm volatile("bar.arrive 2, 256;" ::: "memory");
@@ -255,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       tc_fence_before();                          // S_t reads are complete before the MMA warp overwrites it
       fence_proxy_async_smem();                   // P_t visible to the tensor core (async proxy)
       mbar_arrive(&p_full[t]);
+      if (tr && j < 64) p.trace[j * 8 + 6] = clock64();
       m = mx;
     }
     // last partial product, normalise, store
@@ -297,6 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
 }
 
 }  // namespace
+
+static long long* g_trace = nullptr;
+void fattn_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+long long* fattn_get_trace() { return g_trace; }
 
 cudaError_t fattn_launch(const FattnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
