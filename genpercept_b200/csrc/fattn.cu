@@ -24,6 +24,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -45,6 +46,18 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA pipe for x <= 0: round-to-nearest split x = n + f, |f| <= 0.5 (magic-number add), cubic
+// minimax 2^f (max relative error 7.5e-5, below the 16-bit rounding of P), n added into the exponent
+// field.  Used for one element in four of softmax pass 2, which is otherwise bound by the 16 ex2/clk/SM
+// MUFU rate (10 issue slots vs 2, so the split that balances MUFU and issue is ~1:3).
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float magic = 12582912.f;              // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float r = x + magic;
+  const float f = x - (r - magic);
+  const float pl = fmaf(fmaf(fmaf(0.0551716685f, f, 0.242611125f), f, 0.693260968f), f, 0.999928057f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(r) << 23));
+}
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack16(float a, float b) {
   if constexpr (BF16) {
@@ -62,7 +75,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool BF16>
+template <bool BF16, bool POLY>
 __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constant__ FattnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -79,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
   uint64_t* o_full = p_full + 2;                    // [tile][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int pairs = (p.q_tiles + 1) >> 1;
   const int qp = blockIdx.x % pairs;
   const int bh = blockIdx.x / pairs;
@@ -104,33 +117,47 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    mbar_expect_tx(q_full, (uint32_t)(ntile * kQBytes));
-    for (int t = 0; t < ntile; ++t) tma_load_3d(sQ + t * kQBytes, &p.tmQ, q_full, head * 64, (2 * qp + t) * 128, b);
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(q_full, (uint32_t)(ntile * kQBytes));
+      for (int t = 0; t < ntile; ++t) tma_load_3d(sQ + t * kQBytes, &p.tmQ, q_full, head * 64, (2 * qp + t) * 128, b);
+    }
     for (int j = 0; j < nblk; ++j) {
       const int st = j % kStages;
       mbar_wait(&kv_empty[st], ((j / kStages) & 1) ^ 1, 10);
-      mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
-      tma_load_3d(sK + st * kKBytes, &p.tmK, &kv_full[st], head * 64, j * 128, b);
-      tma_load_3d(sV + st * kVBytes, &p.tmV, &kv_full[st], j * 128, head * 64, b);
-      tma_load_3d(sV + st * kVBytes + 8192, &p.tmV, &kv_full[st], j * 128 + 64, head * 64, b);
+      if (leader) {
+        mbar_expect_tx(&kv_full[st], kKBytes + kVBytes);
+        tma_load_3d(sK + st * kKBytes, &p.tmK, &kv_full[st], head * 64, j * 128, b);
+        tma_load_3d(sV + st * kVBytes, &p.tmV, &kv_full[st], j * 128, head * 64, b);
+        tma_load_3d(sV + st * kVBytes + 8192, &p.tmV, &kv_full[st], j * 128 + 64, head * 64, b);
+      }
+      __syncwarp();
     }
-  } else if ((warp == 9 || warp == 10) && lane == 0 && (warp - 9) < ntile) {
-    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile A, warp 3 -> tile B
-    // One issuing thread per tile: the 32-cycle 128x64x16 P.V instructions are issue-bound from a single
-    // thread, and a shared issuer made each tile wait behind the other's instruction stream.  The next
-    // score tile S_t,j+1 is issued before the P.V product of block j (the softmax warps idle until it lands).
+  } else if ((warp == 9 || warp == 10) && (warp - 9) < ntile) {
+    // ------------------------------------------------------------------ MMA issuers: warp 9 -> tile A, warp 10 -> tile B
+    // One issuing warp per tile (a shared issuer made each tile wait behind the other's instruction
+    // stream).  The whole warp runs the loop and waits on the barriers; one elected lane issues, so the
+    // descriptors live in uniform registers.  The next score tile S_t,j+1 is issued before the P.V product
+    // of block j (the softmax warps idle until it lands).
     const int t = warp - 9;
+    const bool leader = elect_one();
     const uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);
     const uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0);
     const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ + t * kQBytes));
-    const uint32_t p_base = smem_u32(sP + t * kPBytes);
-    auto mma_s = [&](int j) {                 // S_t = Q_t K_j^T
-      const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK + (j % kStages) * kKBytes));
+    const uint64_t p_desc = make_sw128_kmajor_desc(smem_u32(sP + t * kPBytes));
+    const uint64_t k_desc0 = make_sw128_kmajor_desc(smem_u32(sK));
+    const uint64_t v_desc0 = make_sw128_kmajor_desc(smem_u32(sV));
+    const uint32_t s_tmem = tmem_base + t * 128;
+    auto mma_s = [&](int st) {                // S_t = Q_t K_j^T
+      const uint64_t k_desc = k_desc0 + (uint64_t)(st * (kKBytes >> 4));
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k ? 1u : 0u);
-      umma_commit(&s_full[t]);
+        for (int k = 0; k < 4; ++k) umma_f16(s_tmem, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
     };
     mbar_wait(q_full, 0, 12);
     mbar_wait(&kv_full[0], 0, 11);
@@ -142,22 +169,24 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1, 11);
         tc_fence_after();
       }
-      const bool trm = p.trace != nullptr && blockIdx.x == 0 && t == 0 && j < 64;
+      const bool trm = p.trace != nullptr && blockIdx.x == 0 && t == 0 && j < 64 && leader;
       if (trm) p.trace[512 + j * 4 + 0] = clock64();
       mbar_wait(&p_full[t], j & 1, 13);       // P_t,j is in shared memory and S_t has been consumed
       tc_fence_after();
       if (trm) p.trace[512 + j * 4 + 1] = clock64();
-      if (j + 1 < nblk) mma_s(j + 1);
+      if (j + 1 < nblk) mma_s((j + 1) % kStages);
       if (trm) p.trace[512 + j * 4 + 2] = clock64();
-      const uint32_t v_base = smem_u32(sV + st * kVBytes);
+      const uint64_t v_desc = v_desc0 + (uint64_t)(st * (kVBytes >> 4));
+      const uint32_t o_tmem = tmem_base + kOCol + t * 128 + (j & 1) * 64;
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint64_t a = make_sw128_kmajor_desc(p_base + (kk >> 2) * 16384) + 2 * (kk & 3);
-        const uint64_t bd = make_sw128_kmajor_desc(v_base + (kk >> 2) * 8192) + 2 * (kk & 3);
-        umma_f16(tmem_base + kOCol + t * 128 + (j & 1) * 64, a, bd, idesc_o, kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(o_tmem, p_desc + (uint64_t)((kk >> 2) * (16384 >> 4) + 2 * (kk & 3)),
+                   v_desc + (uint64_t)((kk >> 2) * (8192 >> 4) + 2 * (kk & 3)), idesc_o, kk ? 1u : 0u);
+        umma_commit(&o_full[t * 2 + (j & 1)]);
+        umma_commit(&kv_empty[st]);           // this tile has issued every use of block j (barrier counts both tiles)
       }
-      umma_commit(&o_full[t * 2 + (j & 1)]);
-      umma_commit(&kv_empty[st]);             // this tile has issued every use of block j (barrier counts both tiles)
+      __syncwarp();
       if (trm) p.trace[512 + j * 4 + 3] = clock64();
     }
   } else if (warp < 8 && (warp >> 2) < ntile) {
@@ -245,7 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         float pv[32];
         if (kvalid == 128) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) pv[q] = ex2(__uint_as_float(cur[q]) * c2 - mb);
+          for (int q = 0; q < 32; ++q) {
+            const float x = __uint_as_float(cur[q]) * c2 - mb;
+            pv[q] = (POLY && (q & 3) == 3) ? ex2_fma(x) : ex2(x);
+          }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q) pv[q] = (c * 32 + q < kvalid) ? ex2(__uint_as_float(cur[q]) * c2 - mb) : 0.f;
@@ -318,19 +350,27 @@ long long* fattn_get_trace() { return g_trace; }
 
 cudaError_t fattn_launch(const FattnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
+  static bool poly = true;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
+    const void* fns[4] = {(const void*)fattn_kernel<false, false>, (const void*)fattn_kernel<false, true>,
+                          (const void*)fattn_kernel<true, false>, (const void*)fattn_kernel<true, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) return e;
+    }
+    const char* env = getenv("GP_FATTN_POLY");   // 0: every exp2 on the MUFU (A/B switch)
+    if (env && env[0] == '0') poly = false;
     attr_set = true;
   }
   const int grid = p.B * p.heads * ((p.q_tiles + 1) / 2);
   if (grid <= 0) return cudaSuccess;
-  if (p.bf16)
-    fattn_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else
-    fattn_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+  if (p.bf16) {
+    if (poly) fattn_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(p);
+    else fattn_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+  } else {
+    if (poly) fattn_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(p);
+    else fattn_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

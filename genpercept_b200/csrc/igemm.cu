@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sacc = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][Cout][2], only with p.stats
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -341,8 +341,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4 && lane == 0) {
+  // Single-thread roles run warp-uniform (every lane walks the loop and waits on the barriers) and one
+  // elected lane issues: the TMA coordinates / UMMA descriptors then stay in uniform registers.
+  if (warp == 4) {
     // ===================================================================== TMA producer A
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -358,14 +361,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int xs = x0 + sg.dx, ys = y0 + sg.dy;
         for (int c = 0; c < sg.nchunks; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
-          tma_load_4d(smem + stage * stage_bytes, tm, &full_bar[stage], a_k0 + c * kBK, xs, ys, a_n);
+          if (leader) {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
+            tma_load_4d(smem + stage * stage_bytes, tm, &full_bar[stage], a_k0 + c * kBK, xs, ys, a_n);
+          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 7 && lane == 0) {
+  } else if (warp == 7) {
     // ===================================================================== TMA producer B
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t b_bytes = (uint32_t)p.BN * 128;
@@ -378,12 +385,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int nkb = p.nkb[cls];
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 5);
-        mbar_expect_tx(&full_bar[stage], b_bytes);
-        tma_load_3d(smem + stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], b_bytes);
+          tma_load_3d(smem + stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+        }
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if ((warp == 5 || (warp == 6 && p.MT == 2)) && lane == 0) {
+  } else if (warp == 5 || (warp == 6 && p.MT == 2)) {
+    const bool leader = elect_one();
     // ===================================================================== MMA issuer(s)
     // With two accumulator tiles (MT = 2, BN <= 128) each tile gets its own issuing thread: a single
     // thread cannot issue one 64-cycle 128x128x16 MMA every 64 cycles once descriptor arithmetic and
@@ -406,18 +417,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
         const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_bytes);
-        for (int h = h_lo; h < h_hi; ++h) {
-          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + h * kABytes);
+        if (leader) {
+          for (int h = h_lo; h < h_hi; ++h) {
+            const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + h * kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
-            umma_f16(d_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
+              umma_f16(d_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[acc]);
+      if (leader) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -603,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 6) {
-    __syncwarp();          // lane 0 may come from the MMA-issuer branch: reconverge before the .aligned dealloc
+    __syncwarp();          // reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -635,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sacc = reinterpret_cast<float*>(tmem_slot + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int pw = p.TW + 2;                           // patch width in pixels
   const uint32_t patch_bytes = (uint32_t)(pw * (p.TH + 2) * 128);
@@ -654,8 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 4) {
     // ===================================================================== patch producer
+    const bool leader = elect_one();
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -663,13 +679,17 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
       const int x0 = t.tx * p.TW - 1, y0 = t.ty * p.TH - 1;
       for (int kc = 0; kc < p.kc_count; ++kc) {
         mbar_wait(&a_empty[slot], phase ^ 1, 1);
-        mbar_expect_tx(&a_full[slot], patch_bytes);
-        tma_load_4d(smem + slot * p.a_slot_bytes, &p.tmPatch, &a_full[slot], kc * kBK, x0, y0, t.z1);
+        if (leader) {
+          mbar_expect_tx(&a_full[slot], patch_bytes);
+          tma_load_4d(smem + slot * p.a_slot_bytes, &p.tmPatch, &a_full[slot], kc * kBK, x0, y0, t.z1);
+        }
+        __syncwarp();
         if (++slot == 2) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 7 && lane == 0) {
+  } else if (warp == 7) {
     // ===================================================================== weight producer
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -678,14 +698,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
       for (int kc = 0; kc < p.kc_count; ++kc) {
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[stage], phase ^ 1, 5);
-          mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
-          tma_load_3d(sB + stage * b_bytes, &p.tmB, &b_full[stage], (tap * p.kc_count + kc) * kBK, b_row, 0);
+          if (leader) {
+            mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+            tma_load_3d(sB + stage * b_bytes, &p.tmB, &b_full[stage], (tap * p.kc_count + kc) * kBK, b_row, 0);
+          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if ((warp == 5 || warp == 6) && lane == 0) {
+  } else if (warp == 5 || warp == 6) {
     // ===================================================================== MMA issuers (one per image row h)
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
     const int h = warp - 5;
     int slot = 0, stage = 0;
@@ -708,19 +732,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
           mbar_wait(&b_full[stage], b_phase, 6);
           tc_fence_after();
           const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * b_bytes));
-          {
+          if (leader) {
             const uint64_t a_desc = make_sw128_kmajor_desc(patch + tap_off[tap] + h * pw * 128);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               umma_f16(d_tmem + h * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) ? 1u : 0u);
+            umma_commit(&b_empty[stage]);
           }
-          umma_commit(&b_empty[stage]);
+          __syncwarp();
           if (++stage == stages) { stage = 0; b_phase ^= 1; }
         }
-        umma_commit(&a_empty[slot]);
+        if (leader) umma_commit(&a_empty[slot]);
+        __syncwarp();
         if (++slot == 2) { slot = 0; a_phase ^= 1; }
       }
-      umma_commit(&tfull_bar[acc]);
+      if (leader) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -731,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 6) {
-    __syncwarp();          // lane 0 may come from the MMA-issuer branch: reconverge before the .aligned dealloc
+    __syncwarp();          // reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
