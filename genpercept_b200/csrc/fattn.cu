@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
   uint64_t* s_free = s_full + 2;                    // [tile]  S_t,j is in registers          (128 arrivals)
   uint64_t* p_full = s_free + 2;                    // [tile]  P_t,j is in shared memory, O_t rescaled if needed (128)
   uint64_t* o_full = p_full + 2;                    // [tile]  O_t += P_t,j V_j has completed  (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* pp = o_full + 2;                        // [tile]  the other tile has finished an exponential pass (128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp + 2);
 
   const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int pairs = (p.q_tiles + 1) >> 1;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
       mbar_init(&s_free[i], 128);
       mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
+      mbar_init(&pp[i], 128);
     }
     fence_barrier_init();
   }
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     int js = 1, jp = 0;
     long long t_progress = clock64();
     while (jp < nblk) {
-      bool s_ok = js < nblk && mbar_try_wait(&s_free[t], (js - 1) & 1);
+      bool s_ok = js < nblk && mbar_test_wait(&s_free[t], (js - 1) & 1);
       s_ok = __all_sync(0xffffffffu, s_ok);
       if (s_ok) {                             // the softmax warps hold S_t,js-1 in registers
         tc_fence_after();
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         t_progress = clock64();
         continue;
       }
-      bool p_ok = mbar_try_wait(&p_full[t], jp & 1);
+      bool p_ok = mbar_test_wait(&p_full[t], jp & 1);
       p_ok = __all_sync(0xffffffffu, p_ok);
       if (p_ok) {                             // P_t,jp is in shared memory (and O_t rescaled if it had to be)
         tc_fence_after();
@@ -226,6 +228,16 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
     const uint32_t ts = tmem_base + lane_off + t * 128;
     const uint32_t to = tmem_base + lane_off + kOCol + t * 64;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && t == 0 && wq == 0 && lane == 0;
+    // Phase relation of the two tiles.  Left alone they run in lock-step: both exponential passes share the
+    // MUFU (2 x 128 x 8 cycles per sub-partition) and both idle it together during the rest of the block
+    // (r1j: 3700 cycles per block).  With strict alternation (A_j, B_j, A_j+1, ...; two mbarriers) one
+    // tile's load / max / wait phases run under the other's exponentials: 3200 cycles, 11.7 -> 9.8 ms
+    // per step.  `stagger` (a start offset for tile B) is the cheaper idea that did not hold the phase.
+    const bool pingpong = p.pingpong && ntile == 2;
+    if (t == 1 && p.stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) {}
+    }
     for (int j = 0; j < nblk; ++j) {
       if (tr && j < 64) p.trace[j * 8 + 0] = clock64();
       mbar_wait(&s_full[t], j & 1, 15);
@@ -280,6 +292,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         l *= alpha;
         m = mx;
       }
+      if (pingpong) {                              // A_j after B_j-1, B_j after A_j
+        if (t == 0) { if (j > 0) mbar_wait(&pp[0], (j - 1) & 1, 18); }
+        else mbar_wait(&pp[1], j & 1, 18);
+      }
       if (tr && j < 64) p.trace[j * 8 + 4] = clock64();
       // probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
       const float mb = m * c2;
@@ -302,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
                        pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
       l += (l0 + l1) + (l2 + l3);
+      if (pingpong) mbar_arrive(&pp[1 - t]);
       if (tr && j < 64) p.trace[j * 8 + 5] = clock64();
       tc_fence_before();                          // the O_t rescale (if any) is ordered before the next P.V
       fence_proxy_async_smem();                   // P_t visible to the tensor core (async proxy)
@@ -347,10 +364,11 @@ static long long* g_trace = nullptr;
 void fattn_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 long long* fattn_get_trace() { return g_trace; }
 
-cudaError_t fattn_launch(const FattnParams& p, cudaStream_t stream) {
+cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
   static bool attr_set = false;
   static bool poly = false;
   static bool v1 = false;
+  static int stagger = 0, pingpong = 1;
   if (!attr_set) {
     const void* fns[4] = {(const void*)fattn_kernel<false, false>, (const void*)fattn_kernel<false, true>,
                           (const void*)fattn_kernel<true, false>, (const void*)fattn_kernel<true, true>};
@@ -362,9 +380,16 @@ cudaError_t fattn_launch(const FattnParams& p, cudaStream_t stream) {
     if (env && env[0] == '1') poly = true;
     env = getenv("GP_FATTN_V1");                 // 1: the first version of the kernel (fattn_v1.cu), for A/B runs
     if (env && env[0] == '1') v1 = true;
+    env = getenv("GP_FATTN_STAGGER");            // cycles (experiment)
+    if (env) stagger = atoi(env);
+    env = getenv("GP_FATTN_PP");                 // 0: let the exponential passes of the two tiles overlap (A/B switch)
+    if (env && env[0] == '0') pingpong = 0;
     attr_set = true;
   }
-  if (v1) return fattn_v1_launch(p, stream);
+  if (v1) return fattn_v1_launch(p_in, stream);
+  FattnParams p = p_in;
+  p.stagger = stagger;
+  p.pingpong = pingpong;
   const int grid = p.B * p.heads * ((p.q_tiles + 1) / 2);
   if (grid <= 0) return cudaSuccess;
   if (p.bf16) {

@@ -51,6 +51,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time before it answers
+// "not yet": ~8700 cycles measured, r1j — useless for an event loop that watches two barriers).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin with a watchdog: a protocol bug must become a trap (reported CUDA error), never a hang of
 // the GPU box.  1e11 cycles is ~1 minute: far beyond any correct wait, yet tolerant of ncu's
 // instrumented replay passes (a 2 s limit fired under `ncu --set full`).
