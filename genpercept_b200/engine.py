@@ -67,6 +67,11 @@ def lib():
     L.gp_bilinear_up2x.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     L.gp_bench_conv.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double),
                                 POINTER(c_double)]
+    L.gp_resize_aa.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_void_p]
+    L.gp_colorize.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_int,
+                              c_void_p]
+    L.gp_quantize.argtypes = [c_void_p, c_int, c_size_t, c_int, c_void_p, c_int, c_void_p]
     _lib = L
     return L
 
@@ -262,6 +267,59 @@ def bilinear_up2x(x_nhwc):
                                 c_void_p(y.data_ptr()), _stream_ptr())
     _check_free(st, "gp_bilinear_up2x")
     return y
+
+
+RESIZE_MODES = {"bilinear": 0, "bicubic": 1}
+
+
+def resize_aa(x, out_h, out_w, mode="bilinear", device=None):
+    """torchvision ``resize(tensor, [out_h, out_w], interpolation, antialias=True)`` on the GPU
+    (gp_resize_aa).  x: [..., H, W] uint8 or float32, cuda or cpu; the result lives where x lives
+    unless `device` says otherwise ("cuda" uploads a host image and keeps the result on the GPU)."""
+    assert x.dtype in (torch.uint8, torch.float32) and x.dim() >= 2
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    N = x.numel() // (H * W)
+    out_dev = x.device if device is None else torch.device(device)
+    if out_dev.type == "cuda" and out_dev.index is None:
+        out_dev = torch.device("cuda", torch.cuda.current_device())
+    y = torch.empty(tuple(x.shape[:-2]) + (out_h, out_w), dtype=x.dtype, device=out_dev)
+    st = lib().gp_resize_aa(c_void_p(x.data_ptr()), _gp_dtype(x.dtype), 0 if x.is_cuda else 1, N, H, W,
+                            c_void_p(y.data_ptr()), _gp_dtype(y.dtype), 0 if y.is_cuda else 1, out_h, out_w,
+                            RESIZE_MODES[mode], _stream_ptr())
+    _check_free(st, "gp_resize_aa")
+    return y
+
+
+def colorize(pred, lut_u8, vmin=0.0, vmax=1.0, to_host=True):
+    """pred: float32 [B,H,W] (cuda or cpu) -> uint8 [B,H,W,3] through a 256x3 uint8 LUT (gp_colorize)."""
+    assert pred.dtype == torch.float32 and pred.dim() == 3
+    pred = pred.contiguous()
+    B, H, W = pred.shape
+    lut = np.ascontiguousarray(lut_u8, dtype=np.uint8)
+    assert lut.shape == (256, 3)
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cpu" if to_host else pred.device)
+    st = lib().gp_colorize(c_void_p(pred.data_ptr()), 0 if pred.is_cuda else 1, B, H, W, vmin, vmax,
+                           lut.ctypes.data_as(c_void_p), c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, _stream_ptr())
+    _check_free(st, "gp_colorize")
+    return out
+
+
+def quantize(pred, bits=16, to_host=True):
+    """(pred * 65535).astype(uint16) / (pred * 255).astype(uint8) (gp_quantize); uint16 comes back as int16 storage
+    viewed through numpy on the host."""
+    assert pred.dtype == torch.float32 and bits in (8, 16)
+    pred = pred.contiguous()
+    if to_host:
+        out = np.empty(tuple(pred.shape), dtype=np.uint16 if bits == 16 else np.uint8)
+        ptr, on_host = out.ctypes.data_as(c_void_p), 1
+    else:
+        out = torch.empty(tuple(pred.shape), dtype=torch.uint16 if bits == 16 else torch.uint8, device=pred.device)
+        ptr, on_host = c_void_p(out.data_ptr()), 0
+    st = lib().gp_quantize(c_void_p(pred.data_ptr()), 0 if pred.is_cuda else 1, pred.numel(), bits, ptr, on_host,
+                           _stream_ptr())
+    _check_free(st, "gp_quantize")
+    return out
 
 
 def bench_conv(dtype, N, H, W, Cin, Cout, ks=3, mode=0, iters=10):

@@ -20,9 +20,10 @@ import torch
 from PIL import Image
 from torchvision.transforms.functional import pil_to_tensor, resize
 
+from . import engine as E
 from . import weights as W
 from .engine import Engine
-from .image_util import chw2hwc, colorize_depth_maps, get_tv_resample_method, resize_max_res
+from .image_util import _lut, get_tv_resample_method, resize_max_res
 
 ONE_CHANNEL_MODES = ("depth", "matting", "dis", "disparity")     # genpercept_pipeline.py:523
 
@@ -234,33 +235,42 @@ class GenPerceptPipeline:
             raise TypeError(f"Unknown input type: {type(input_image) = }")
         input_size = rgb.shape
         assert 4 == rgb.dim() and 3 == input_size[-3], f"Wrong input shape {input_size}, expected [1, rgb, H, W]"
-        if processing_res > 0:
-            rgb = resize_max_res(rgb, max_edge_resolution=processing_res, resample_method=resample)
+        # Pre/post-processing runs on the GPU (gp_resize_aa / gp_colorize / gp_quantize) for the
+        # anti-aliased bilinear / bicubic filters; the nearest modes keep torchvision's host path.
+        gpu_resample = resample_method in E.RESIZE_MODES
         if rgb.dtype != torch.uint8:
             assert rgb.min() >= 0 and rgb.max() <= 255
-            rgb = rgb.round().clamp(0, 255).to(torch.uint8) if rgb.is_floating_point() else rgb.to(torch.uint8)
-        # normalisation x/255*2-1 and the cast to self.dtype (:245-246) happen inside the engine
+            rgb = rgb.float() if rgb.is_floating_point() else rgb.to(torch.uint8)
+        if processing_res > 0:
+            if gpu_resample:
+                h0, w0 = rgb.shape[-2:]
+                f = min(processing_res / w0, processing_res / h0)                    # image_util.py:98-102
+                rgb = E.resize_aa(rgb, int(h0 * f), int(w0 * f), resample_method, device=self.device)
+            else:
+                rgb = resize_max_res(rgb, max_edge_resolution=processing_res, resample_method=resample)
+        if rgb.dtype != torch.uint8:                       # float image in [0,255]: the reference keeps it float (:245)
+            rgb = rgb.to(self.device) / 255.0 * 2.0 - 1.0
+        # for uint8 the normalisation x/255*2-1 and the cast to self.dtype (:245-246) happen inside the engine
         pred = self.single_infer(rgb, num_inference_steps=denoising_steps, generator=generator,
                                  show_pbar=show_progress_bar, fix_timesteps=fix_timesteps, prompt=prompt, mode=mode)
         if match_input_res and tuple(pred.shape[-2:]) != tuple(input_size[-2:]):
-            pred = resize(pred, list(input_size[-2:]), interpolation=resample, antialias=True)
-        batched = pred.shape[0] > 1
-        pred_np = pred.cpu().numpy()
-        pred_np = pred_np.squeeze() if not batched else (pred_np[:, 0] if pred_np.shape[1] == 1 else pred_np)
-        pred_np = pred_np.clip(0, 1)
-        items = [pred_np] if not batched else list(pred_np)
-        colored = []
-        for p in items:
-            if color_map is not None:
-                assert self.mode in ["depth", "disparity"]
-                c = colorize_depth_maps(p, 0, 1, cmap=color_map).squeeze()
-                c = (c * 255).astype(np.uint8)
-                colored.append(Image.fromarray(chw2hwc(c)))
+            if gpu_resample:
+                pred = E.resize_aa(pred, int(input_size[-2]), int(input_size[-1]), resample_method)
             else:
-                c = (p * 255.0).astype(np.uint8)
-                if c.ndim == 3 and c.shape[0] == 3:
-                    c = np.transpose(c, (1, 2, 0))
-                colored.append(Image.fromarray(c))
+                pred = resize(pred, list(input_size[-2:]), interpolation=resample, antialias=True)
+        pred = pred.clamp(0, 1)                            # :310 (a bicubic resize can overshoot)
+        batched = pred.shape[0] > 1
+        one_ch = pred.shape[1] == 1
+        if color_map is not None:
+            assert self.mode in ["depth", "disparity"]
+            lut = (_lut(color_map) * 255).astype(np.uint8)                          # (c * 255).astype(uint8), :318-321
+            col = E.colorize(pred[:, 0].contiguous(), lut, 0.0, 1.0).numpy()      # [B,H,W,3] uint8 on the host
+        else:
+            col = E.quantize(pred, 8)                                               # (p * 255).astype(uint8)
+            col = col[:, 0] if one_ch else np.transpose(col, (0, 2, 3, 1))
+        colored = [Image.fromarray(c) for c in col]
+        pred_np = pred.cpu().numpy()
+        pred_np = pred_np.squeeze() if not batched else (pred_np[:, 0] if one_ch else pred_np)
         if batched:
             if pred_np.ndim == 4 and pred_np.shape[1] == 3:
                 pred_np = np.transpose(pred_np, (0, 2, 3, 1))

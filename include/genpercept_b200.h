@@ -106,6 +106,21 @@ gp_status gp_layernorm(int dtype, const void* x, int64_t tokens, int C, const fl
 gp_status gp_attention(int dtype, const void* q, const void* k, const void* v, int B, int T, int heads, int d,
                        float scale, void* o, void* stream);
 gp_status gp_bilinear_up2x(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
+/* ---- pre/post-processing around the hot path; buffers may be host or device ------------
+ * gp_resize_aa replaces torchvision.transforms.functional.resize(tensor, size, interpolation, antialias=True)
+ * as called by resize_max_res (/root/reference/genpercept/util/image_util.py:75-105) and by the resize back
+ * to the input resolution (/root/reference/genpercept/genpercept_pipeline.py:301-307): N planes [N,H,W] ->
+ * [N,OH,OW]; src GP_U8 or GP_F32; dst GP_F32, or GP_U8 = round-half-even (+ clamp for bicubic) as torchvision
+ * does for integer tensors; mode 0 bilinear, 1 bicubic. */
+gp_status gp_resize_aa(const void* src, int src_dtype, int src_on_host, int N, int H, int W, void* dst, int dst_dtype,
+                       int dst_on_host, int OH, int OW, int mode, void* stream);
+/* colorize_depth_maps + the uint8 cast at its call site (image_util.py:25-63, genpercept_pipeline.py:318-321):
+ * pred f32 [B,H,W] -> u8 [B,H,W,3] = lut[clip(floor((x-vmin)/(vmax-vmin)*256), 0, 255)], lut = 256x3 u8 (host). */
+gp_status gp_colorize(const float* pred, int pred_on_host, int B, int H, int W, float vmin, float vmax,
+                      const uint8_t* lut768_host, uint8_t* out_hwc, int out_on_host, void* stream);
+/* (pred*255).astype(uint8) / (pred*65535).astype(uint16) of /root/reference/run.py:449-455; bits = 8 or 16. */
+gp_status gp_quantize(const float* pred, int pred_on_host, size_t n, int bits, void* out, int out_on_host, void* stream);
+
 /* time one igemm configuration: returns average microseconds over `iters` launches */
 gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int ks, int mode, int iters,
                         double* usec, double* flops);
