@@ -263,6 +263,15 @@ def main():
                     "peak_source": pk["src"],
                     "how": "sum(algorithmic FLOPs of every igemm launch in a step) / sum(CUDA-event duration of "
                            "those launches), one extra warm step with events around each op on the launch stream"}
+        # DRAM bytes actually moved by those launches: one ncu pass over every launch of a warm step of THIS
+        # workload (scripts/prof_step.py, committed summary); valid for the default workload only.
+        tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_final_step_dram.json")
+        if os.path.exists(tf) and B == 8 and R == 768 and args.readout == "vae" and len(ig) > 0:
+            sd = json.load(open(tf))
+            if sd.get("igemm_launches") == len(ig):
+                roofline["traffic"] = sd["igemm_dram_bytes"] / len(ig)
+                roofline["traffic_unit"] = "bytes per launch (mean over the step's igemm launches; ncu dram__bytes_read+write)"
+                roofline["algorithmic_bytes_per_launch"] = sum(o["bytes"] for o in ig) / len(ig)
         if args.ops_json:
             json.dump(ops, open(args.ops_json, "w"), indent=1)
 

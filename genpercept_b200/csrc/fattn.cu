@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
         else mbar_wait(&pp[1], j & 1, 18);
       }
       if (tr && j < 64) p.trace[j * 8 + 4] = clock64();
-      // probabilities -> shared memory (A operand of P.V), row sum (4 partial sums)
+      // probabilities -> shared memory (A operand of P.V), row sum (8 partial sums)
       const float mb = m * c2;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f, l5 = 0.f, l6 = 0.f, l7 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float pv[32];
@@ -309,7 +309,10 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
           pv[q] = (POLY && (q & 3) == 3) ? ex2_fma(x) : ex2(x);
         }
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) { l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3]; }
+        for (int q = 0; q < 32; q += 8) {
+          l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3];
+          l4 += pv[q + 4]; l5 += pv[q + 5]; l6 += pv[q + 6]; l7 += pv[q + 7];
+        }
         const uint32_t dst = prow + (c >> 1) * 16384;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
                        pack16<BF16>(pv[8 * i + 2], pv[8 * i + 3]), pack16<BF16>(pv[8 * i + 4], pv[8 * i + 5]),
                        pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
-      l += (l0 + l1) + (l2 + l3);
+      l += ((l0 + l1) + (l2 + l3)) + ((l4 + l5) + (l6 + l7));
       if (pingpong) mbar_arrive(&pp[1 - t]);
       if (tr && j < 64) p.trace[j * 8 + 5] = clock64();
       tc_fence_before();                          // the O_t rescale (if any) is ordered before the next P.V

@@ -80,6 +80,52 @@ def launches_table(tag):
     return "\n".join(out)
 
 
+def step_dram(tag):
+    """Per-launch DRAM traffic of ONE warm step (scripts/prof_step.py under ncu): totals by kernel, and the
+    igemm total next to the algorithmic bytes of the same launches (ops.json)."""
+    f = os.path.join(G, "step_dram.csv")
+    if not os.path.exists(f):
+        return ""
+    lines = [l for l in open(f) if l.startswith('"')]
+    r = list(csv.reader(lines))
+    if len(r) < 10:
+        return ""
+    idx = {h: i for i, h in enumerate(r[0])}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3,
+             "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+    tot = collections.defaultdict(lambda: [set(), 0.0, 0.0, 0.0])
+    for d in r[1:]:
+        try:
+            v = float(d[idx["Metric Value"]].replace(",", "")) * scale.get(d[idx["Metric Unit"]], 1)
+        except Exception:
+            continue
+        n = re.sub(r"\(.*", "", d[idx["Kernel Name"]]).replace("void unnamed>::", "").replace("unnamed>::", "")
+        t = tot[n]
+        t[0].add(d[idx["ID"]])
+        m = d[idx["Metric Name"]]
+        if m == "dram__bytes_read.sum": t[1] += v
+        elif m == "dram__bytes_write.sum": t[2] += v
+        elif m == "gpu__time_duration.sum": t[3] += v
+    out = ["DRAM traffic of one warm step, every launch (`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, "
+           "`scripts/prof_step.py`):", "", "| kernel | launches | DRAM read GB | DRAM write GB | time ms (under ncu) |",
+           "|---|---|---|---|---|"]
+    for k, v in sorted(tot.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
+        out.append(f"| `{k}` | {len(v[0])} | {v[1] / 1e9:.2f} | {v[2] / 1e9:.2f} | {v[3] * 1e3:.2f} |")
+    ig = [v for k, v in tot.items() if "igemm" in k]
+    res = {"igemm_launches": sum(len(v[0]) for v in ig), "igemm_dram_bytes": sum(v[1] + v[2] for v in ig),
+           "all_dram_bytes": sum(v[1] + v[2] for v in tot.values())}
+    of = os.path.join(G, "ops.json")
+    if os.path.exists(of):
+        ops = json.load(open(of))
+        res["igemm_algorithmic_bytes"] = sum(o["bytes"] for o in ops if o.get("kind") == 1)
+        res["all_nominal_bytes"] = sum(o["bytes"] for o in ops)
+        out += ["", f"igemm launches: measured DRAM {res['igemm_dram_bytes'] / 1e9:.2f} GB per step vs "
+                f"{res['igemm_algorithmic_bytes'] / 1e9:.2f} GB algorithmic (inputs + outputs + weights once per launch); "
+                f"whole step {res['all_dram_bytes'] / 1e9:.2f} GB measured vs {res['all_nominal_bytes'] / 1e9:.2f} GB nominal."]
+    json.dump(res, open(os.path.join(P, f"{tag}_step_dram.json"), "w"), indent=1)
+    return "\n".join(out)
+
+
 KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -132,6 +178,7 @@ def main():
             shutil.copy(os.path.join(G, name), os.path.join(P, f"{tag}_{name}"))
     parts.append(ops_table(tag))
     parts.append(launches_table(tag))
+    parts.append(step_dram(tag))
     parts.append(ncu_extract("prof_igemm.ncu-rep", tag, "igemm",
                              [(3, "conv3x3 128->128 @768x768 B=8 (patch-resident main loop)"),
                               (7, "conv3x3 256->256 @384x384 B=8 (tap-streaming main loop, BN=256)"),
