@@ -296,6 +296,28 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
                              bw, bh, bf16_), name + ": tmap out");
       for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
     }
+    // the residual has the output's shape and addressing: same maps over its base
+    if (a.res1 && !a.res2 && !(a.flags & IG_GEGLU) && std::getenv("GP_NO_RES_TMA") == nullptr) {
+      p.res_tma = 1;
+      const void* rb = ptr(*a.res1);
+      if (tokens) {
+        const long long ntok = (long long)N * H * W;
+        check_cuda(make_tmap_a(&p.tmRes[0], rb, out_c, (int)ntok, 1, 1, out_c, ntok * out_c, ntok * out_c, bw, bh, bf16_),
+                   name + ": tmap res");
+        for (int i = 1; i < 4; ++i) p.tmRes[i] = p.tmRes[0];
+      } else if (a.mode == 3) {
+        for (int c = 0; c < 4; ++c) {
+          const int py = c >> 1, px = c & 1;
+          const uint8_t* ob = reinterpret_cast<const uint8_t*>(rb) + ((long long)py * Wo + px) * out_c * 2;
+          check_cuda(make_tmap_a(&p.tmRes[c], ob, out_c, W, H, N, 2LL * out_c, 2LL * Wo * out_c, (long long)Ho * Wo * out_c, bw, bh,
+                                 bf16_), name + ": tmap res");
+        }
+      } else {
+        check_cuda(make_tmap_a(&p.tmRes[0], rb, out_c, Wo, Ho, N, out_c, (long long)Wo * out_c, (long long)Ho * Wo * out_c,
+                               bw, bh, bf16_), name + ": tmap res");
+        for (int i = 1; i < 4; ++i) p.tmRes[i] = p.tmRes[0];
+      }
+    }
   }
   // patch-resident main loop for the wide-image, narrow-N 3x3 layers
   if (staged && a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && p.MT == 2 && p.TW == 128 && p.TH == 2 &&

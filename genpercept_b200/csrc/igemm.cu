@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "ptx.cuh"
@@ -99,7 +100,7 @@ __device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
 // (warp, 64-channel group), plus the GroupNorm partial sums read back column-wise from the tile.
 template <bool BF16>
 __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, uint64_t* tfull_bar,
-                                                uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane) {
+                                                uint64_t* tempty_bar, uint64_t* res_bar, uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue, staged + TMA store
   // TMEM -> registers (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile ->
   // one TMA store per (warp, 64-channel group): full-line writes instead of 16-byte pieces at a
@@ -111,7 +112,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   const uint32_t my_row = stg_addr + lane * 128;
   const int sw = lane & 7;
   int acc = 0;
-  uint32_t acc_phase = 0;
+  uint32_t acc_phase = 0, res_phase = 0;
   const bool relu = (p.flags & IG_RELU) != 0;
   const bool geglu = (p.flags & IG_GEGLU) != 0;
   const bool do_stats = p.stats != nullptr;
@@ -206,6 +207,21 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
         }
         if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
         __syncwarp();
+        uint4 rt[8];                                          // this thread's residual row (64 channels), res_tma only
+        if (p.res_tma) {
+          if (lane == 0) {
+            mbar_expect_tx(&res_bar[wq], 4096);
+            tma_load_4d(stg, &p.tmRes[cls], &res_bar[wq], n0, sx, sy, t.z1);
+          }
+          mbar_wait(&res_bar[wq], res_phase, 7);
+          res_phase ^= 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rt[i].x), "=r"(rt[i].y), "=r"(rt[i].z), "=r"(rt[i].w)
+                         : "r"(my_row + ((i ^ sw) << 4)));
+          __syncwarp();                                       // every row is in registers before the tile is overwritten
+        }
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -223,7 +239,10 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           }
           uint4 r1[4], r2[4];
           const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
-          if (has1) {
+          if (p.res_tma) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r1[q] = rt[sub * 4 + q];
+          } else if (has1) {
             const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
 #pragma unroll
             for (int q = 0; q < 4; ++q) r1[q] = rp[q];
@@ -316,7 +335,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
   float* sacc = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][Cout][2], only with p.stats
 
   const int warp = uniform_warp_id();
@@ -333,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(&tfull_bar[i], p.MT);
       mbar_init(&tempty_bar[i], 128);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 6) tmem_alloc(tmem_slot, kTmemCols);
@@ -437,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp < 4 && p.tma_store) {
-    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
   } else if (warp < 4) {
     // ===================================================================== epilogue
     const int wq = warp;                     // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
@@ -647,7 +668,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
   uint64_t* b_empty = b_full + stages;
   uint64_t* tfull_bar = b_empty + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
   float* sacc = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = uniform_warp_id();
@@ -661,6 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }        // two MMA issuers
     for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 2); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 6) tmem_alloc(tmem_slot, kTmemCols);
@@ -752,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_patch_kernel(const __grid_c
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp < 4) {
-    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -855,6 +878,10 @@ const char* igemm_finalize(IgemmParams* p) {
       return "patch mode needs the staged epilogue, TW = 128, MT = 2 and a single-source 3x3 tap table";
     p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
     st = (kMaxSmem - 2048 - stats_bytes - 4 * 4096 - 2 * p->a_slot_bytes) / (p->BN * 128);
+    if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
+      const int v = atoi(env);
+      if (v >= 2 && v < st) st = v;
+    }
   }
   if (st > 8) st = 8;
   if (st < 2) return "tile too large for shared memory";

@@ -77,6 +77,11 @@ struct IgemmParams {
   // tensor map).  Needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output.  One map per class.
   int tma_store;
   CUtensorMap tmOut[kMaxClasses];   // (C, W, H, N) views of the output, box (64, min(TW,32), 32/min(TW,32), 1)
+  // Residual through TMA (staged epilogue, res1 only): the same boxes of the residual tensor are LOADED into the
+  // staging tile before the accumulator is read.  Row-per-thread global loads of a residual cost 32 L1 sector
+  // look-ups per warp request (ncu r1k: 58 % tensor pipe with a residual vs 92 % without, same layer).
+  int res_tma;
+  CUtensorMap tmRes[kMaxClasses];
   // Patch-resident main loop (3x3 stride-1, one source, TW = 128, MT = 2, staged epilogue): per
   // 64-channel K chunk ONE (TH+2) x (TW+2) halo patch is loaded and all nine taps are fed from it by
   // row-offset descriptors (tap (dy,dx) starts (h+dy+1)*(TW+2) + dx+1 rows into the patch), instead of
