@@ -77,6 +77,24 @@ __device__ __forceinline__ void add8(float* v, const uint4& u) {
   }
 }
 
+// gelu(g) = g * Phi(g), exact-erf form (what diffusers' GEGLU uses), with erf from Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner instead of erff()'s two-branch
+// polynomial — the GEGLU projection is bound by its epilogue (tensor pipe 33 %, ncu r1_final).
+//   1 - erf(z) = (a1 t + ... + a5 t^5) e^{-z^2},  t = 1 / (1 + p z),  z = |g| / sqrt(2)
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float z = fabsf(g) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q = q * t * e * 0.5f;                                   // = (1 - erf(z)) / 2 = Phi(-|g|)
+  return g * (g >= 0.f ? 1.f - q : q);
+}
+
 // Each lane holds 32 values v[0..32); on return lane i holds in v[0] the sum over all 32 lanes of
 // their v[i] (recursive halving: 16+8+4+2+1 = 31 shuffles, fixed order -> deterministic).
 __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
@@ -186,7 +204,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const float a = __uint_as_float(r[q]) + bz[q], gt = __uint_as_float(r[16 + q]) + bz[16 + q];
-              g[q] = valid ? a * (0.5f * gt * (1.f + erff(gt * 0.70710678118654752f))) : 0.f;
+              g[q] = valid ? a * gelu_erf(gt) : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -591,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             uint16_t* og = reinterpret_cast<uint16_t*>(p.out) + pix_off + (n0 >> 1);
             float g[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) g[q] = v[q] * (0.5f * v[16 + q] * (1.f + erff(v[16 + q] * 0.70710678118654752f)));
+            for (int q = 0; q < 16; ++q) g[q] = v[q] * gelu_erf(v[16 + q]);
 #pragma unroll
             for (int q = 0; q < 16; q += 8) {
               uint4 u;
