@@ -144,13 +144,16 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
   }
 }
 
-__global__ void gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int N, int Ctot, int groups, float inv_count,
-                                   float eps, float* __restrict__ ss) {
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (n, group)
-  if (wid >= N * groups) return;
-  const int n = wid / groups, g = wid % groups;
+// One CTA of 256 threads per (image, group): the partial sums (one slot per producing CTA or pixel chunk, up to
+// 256 x channels-per-group entries) are read with all 8 warps in flight and reduced in a fixed order (thread ->
+// warp shuffle -> 8 warp totals), so the result does not depend on scheduling.  (One WARP per group left the
+// kernel latency-bound on 32 SMs: 113 launches x 16 us = 1.8 ms of a 95 ms step, ncu r1_final.)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int N, int Ctot, int groups,
+                                                          float inv_count, float eps, float* __restrict__ ss) {
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = Ctot / groups;
   const int glo = g * cpg, ghi = glo + cpg;
   float s = 0.f, q = 0.f;
@@ -161,7 +164,7 @@ __global__ void gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __
     const int w = hi - lo;
     if (w > 0) {
       const int entries = w * src.chunks;
-      for (int i = lane; i < entries; i += 32) {
+      for (int i = threadIdx.x; i < entries; i += 256) {
         const int ch = i / w, c = lo - cbase + (i - ch * w);
         const float2 v = *reinterpret_cast<const float2*>(src.partial + (((long long)n * src.chunks + ch) * src.C + c) * 2);
         s += v.x; q += v.y;
@@ -170,10 +173,14 @@ __global__ void gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __
     cbase += src.C;
   }
   s = warp_sum(s); q = warp_sum(q);
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  s = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) + ((red[0][4] + red[0][5]) + (red[0][6] + red[0][7]));
+  q = ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) + ((red[1][4] + red[1][5]) + (red[1][6] + red[1][7]));
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
-  for (int i = lane; i < cpg; i += 32) {
+  for (int i = threadIdx.x; i < cpg; i += 256) {
     const int c = glo + i;
     const float sc = rstd * gamma[c];
     ss[((long long)n * Ctot + c) * 2] = sc;
@@ -601,9 +608,8 @@ cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, 
 cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const float* beta, int N, int Ctot,
                         int groups, long long HW, float eps, float* ss, cudaStream_t s) {
   if (nsrc < 1 || nsrc > 2) return cudaErrorInvalidValue;
-  const int warps = N * groups;
   const float inv_count = 1.0f / ((float)HW * (float)(Ctot / groups));
-  gn_finalize_kernel<<<(warps + 7) / 8, 256, 0, s>>>(srcs[0], nsrc > 1 ? srcs[1] : srcs[0], nsrc, gamma, beta, N, Ctot,
+  gn_finalize_kernel<<<N * groups, 256, 0, s>>>(srcs[0], nsrc > 1 ? srcs[1] : srcs[0], nsrc, gamma, beta, N, Ctot,
                                                        groups, inv_count, eps, ss);
   return cudaGetLastError();
 }
