@@ -9,7 +9,7 @@ timeout 900 python bench.py --ops-json gpurun_out/ops.json > gpurun_out/bench.lo
 echo "bench exit $?"; tail -n 1 gpurun_out/bench.log | cut -c1-400
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
 echo "ref exit $?"; tail -n 1 gpurun_out/bench_ref.log | cut -c1-300
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2800 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu launches exit $?"; wc -l gpurun_out/launches.csv
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -n 2

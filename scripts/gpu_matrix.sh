@@ -10,3 +10,5 @@ run --res 512 --batch 1
 run --res 768 --batch 1
 run --res 1024 --batch 1
 run --cuda-graph
+run --res 768 --batch 1 --cuda-graph
+run --res 384 --batch 1 --cuda-graph
