@@ -19,7 +19,7 @@
 //   saw its maximum grow by more than 2^8 (P <= 256 stays exact enough in 16 bits, sums are fp32).  Only
 //   then the warp rescales its 32 rows of O in TMEM (tcgen05.ld / st).  On most blocks the softmax warps
 //   never touch O, which removes the per-block "wait for P.V, load O, rescale" chain of the first version
-//   (fattn_v1.cu: 4200 cycles per block, of which 1900 outside the exponential pass; r1i trace).
+//   (git history, "fattn_v1": 4200 cycles per block, 1900 of them outside the exponential pass; profiles/README.md §4).
 // One elected lane of each single-thread role issues, the whole warp walks the loop (uniform registers).
 //
 // S and P never touch HBM (the round-1 unfused path wrote both: 4 x T^2 x 2 bytes per head).
@@ -32,8 +32,6 @@
 #include "ptx.cuh"
 
 namespace gp {
-cudaError_t fattn_v1_launch(const FattnParams& p, cudaStream_t stream);   // fattn_v1.cu (A/B reference)
-
 namespace {
 
 constexpr int kThreads = 384;
@@ -370,7 +368,6 @@ long long* fattn_get_trace() { return g_trace; }
 cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
   static bool attr_set = false;
   static bool poly = false;
-  static bool v1 = false;
   static int stagger = 0, pingpong = 1;
   if (!attr_set) {
     const void* fns[4] = {(const void*)fattn_kernel<false, false>, (const void*)fattn_kernel<false, true>,
@@ -381,15 +378,12 @@ cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
     }
     const char* env = getenv("GP_FATTN_POLY");   // 1: a quarter of the exponentials on the FMA pipe (A/B switch)
     if (env && env[0] == '1') poly = true;
-    env = getenv("GP_FATTN_V1");                 // 1: the first version of the kernel (fattn_v1.cu), for A/B runs
-    if (env && env[0] == '1') v1 = true;
     env = getenv("GP_FATTN_STAGGER");            // cycles (experiment)
     if (env) stagger = atoi(env);
     env = getenv("GP_FATTN_PP");                 // 0: let the exponential passes of the two tiles overlap (A/B switch)
     if (env && env[0] == '0') pingpong = 0;
     attr_set = true;
   }
-  if (v1) return fattn_v1_launch(p_in, stream);
   FattnParams p = p_in;
   p.stagger = stagger;
   p.pingpong = pingpong;

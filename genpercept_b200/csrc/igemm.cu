@@ -2,14 +2,17 @@
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over a static round-robin tile list).  The single-thread
 // producer / issuer roles sit in the HIGHEST warp ids (4..7): the SM sub-partition arbiter favours higher warp
-// ids, and an issuer starved by the epilogue warp of its sub-partition stalls the tensor pipe (fattn trace, r1h):
-//   warp 4 lane 0 : TMA producer A (activation box per 64-channel K block, `stages`-deep ring)
-//   warp 7 lane 0 : TMA producer B (weight box per K block) — its own thread: one thread issuing
+// ids, and an issuer starved by the epilogue warp of its sub-partition stalls the tensor pipe (fattn trace, r1h).
+// Each single-thread role is executed by its WHOLE warp (every lane walks the loop and waits on the barriers) and
+// one elect.sync lane issues: coordinates and descriptors stay in uniform registers (back-to-back UTCHMMA).
+//   warp 4        : TMA producer A (activation box per 64-channel K block, `stages`-deep ring)
+//   warp 7        : TMA producer B (weight box per K block) — its own warp: one thread issuing
 //                   both boxes plus the barrier traffic could not keep up with BN=128 tiles
 //                   (ncu r1a: tensor pipe 45 % active on the 128->128 convs, DRAM/L2 not saturated)
-//   warp 5 (6) l.0: MMA issuer    (MT x 4 tcgen05.mma 128xBNx16 per K block; commit frees the slot)
+//   warp 5 (and 6): MMA issuer(s), one per accumulator tile (4 tcgen05.mma 128xBNx16 per K block; commit frees the slot)
 //   warp 6        : TMEM allocator (512 columns = 2 accumulator buffers x MT tiles)
-//   warps 0..3    : epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/residual/act -> HBM)
+//   warps 0..3    : epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias / TMA-loaded residual / act -> staged tile
+//                   -> TMA store, GroupNorm partial sums from the staged tile)
 // MT = 2 (a 256-pixel M tile per CTA, two accumulators sharing every weight box) when BN <= 128:
 // halves the weight traffic and the per-byte barrier / TMA issue cost of the narrow-N layers.
 #include "igemm.h"
@@ -95,20 +98,6 @@ __device__ __forceinline__ float gelu_erf(float g) {
   return g * (g >= 0.f ? 1.f - q : q);
 }
 
-// Each lane holds 32 values v[0..32); on return lane i holds in v[0] the sum over all 32 lanes of
-// their v[i] (recursive halving: 16+8+4+2+1 = 31 shuffles, fixed order -> deterministic).
-__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < off; ++k) {
-      const float send = up ? v[k] : v[k + off];
-      const float keep = up ? v[k + off] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
 __device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }

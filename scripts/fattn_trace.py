@@ -1,6 +1,4 @@
-"""Debug: phase timeline of the fused attention kernel (CTA 0, tile A, row 0) from clock64() stamps.
-
-GP_FATTN_V1=1 selects the first kernel version (different stamp meaning: see TRACE_V1 below)."""
+"""Debug: phase timeline of the fused attention kernel (CTA 0, tile A, row 0) from clock64() stamps."""
 import ctypes
 import os
 import sys
@@ -23,27 +21,16 @@ E.attention(q, k, v, H, D ** -0.5)
 torch.cuda.synchronize()
 t = buf.cpu().tolist()
 L.gp_debug_fattn_trace(None)
-v1 = os.environ.get("GP_FATTN_V1") == "1"
 print("softmax thread (tile A row 0): per-block phase durations in cycles")
-if v1:
-    print("blk  waitS pass1 waitO updO  pass2 fence | period")
-else:
-    print("blk  waitS ld+max waitPV rescale exp+P fence | period")
+print("blk  waitS ld+max waitPV rescale+turn exp+P fence | period")
 for j in range(2, 26):
     s = t[j * 8: j * 8 + 7]
     nxt = t[(j + 1) * 8]
     print(f"{j:3d} {s[1]-s[0]:6d} {s[2]-s[1]:5d} {s[3]-s[2]:5d} {s[4]-s[3]:5d} {s[5]-s[4]:6d} {s[6]-s[5]:5d} | {nxt-s[0]:6d}")
-if v1:
-    print("MMA issuer (tile A): wait p_full, issue S(j+1), issue PV(j)+commits | period")
-    for j in range(2, 12):
-        m = t[512 + j * 4: 512 + j * 4 + 4]
-        nxt = t[512 + (j + 1) * 4]
-        print(f"{j:3d} {m[1]-m[0]:6d} {m[2]-m[1]:5d} {m[3]-m[2]:5d} | {nxt-m[0]:6d}")
-else:
-    print("MMA issuer (tile A), relative to the softmax thread's stamps of the same block j:")
-    print("blk  S(j) issued -> S(j) seen by softmax | P(j) arrive -> PV(j) issue start | PV issue cycles | S(j+1) issued - S(j) loaded")
-    for j in range(2, 12):
-        m = t[512 + j * 4: 512 + j * 4 + 3]
-        m1 = t[512 + (j + 1) * 4]
-        s = t[j * 8: j * 8 + 7]
-        print(f"{j:3d} {s[1]-m[0]:8d} {m[1]-s[6]:8d} {m[2]-m[1]:8d} {m1-s[1]:8d}")
+print("MMA issuer (tile A), relative to the softmax thread's stamps of the same block j:")
+print("blk  S(j) issued -> S(j) seen by softmax | P(j) arrive -> PV(j) issue start | PV issue cycles | S(j+1) issued - S(j) loaded")
+for j in range(2, 12):
+    m = t[512 + j * 4: 512 + j * 4 + 3]
+    m1 = t[512 + (j + 1) * 4]
+    s = t[j * 8: j * 8 + 7]
+    print(f"{j:3d} {s[1]-m[0]:8d} {m[1]-s[6]:8d} {m[2]-m[1]:8d} {m1-s[1]:8d}")
