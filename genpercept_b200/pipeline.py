@@ -128,6 +128,21 @@ class GenPerceptPipeline:
             kw["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
         return cls(torch_dtype=torch_dtype, **kw)
 
+    @classmethod
+    def from_run_args(cls, checkpoint, unet=None, lora_rank=0, **kw):
+        """The model section of the reference CLI (run.py:273-376, infer.py:299-405) in one call:
+        ``--checkpoint`` (SD-2.1 folder), ``--unet`` (fine-tuned UNet folder in either layout, with an optional
+        ``dpt_head_identity/`` or ``vae_decoder/`` + ``vae_post_quant_conv/`` next to it) and ``--lora_rank``.
+        See genpercept_b200/loader.py for the layouts."""
+        from . import loader
+        parts = loader.assemble(checkpoint, unet=unet, lora_rank=lora_rank)
+        root = str(checkpoint)
+        if kw.get("text_embed") is None and kw.get("text_encoder") is None and os.path.isdir(os.path.join(root, "text_encoder")):
+            from transformers import CLIPTextModel, CLIPTokenizer
+            kw["text_encoder"] = CLIPTextModel.from_pretrained(os.path.join(root, "text_encoder"))
+            kw["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
+        return cls(unet=parts["unet"], vae=parts["vae"], customized_head=parts["customized_head"], **kw)
+
     def to(self, *a, **k):
         return self
 
