@@ -164,8 +164,8 @@ struct gp_engine {
   // 3x3 (or 1x1) convolution weights, tap-major, sources concatenated; optional fused 1x1 shortcut
   const PackedW& conv_w(const std::string& key, const std::vector<int>& srcC, const std::string& sc_key = "",
                         const std::vector<int>& scC = {}, const std::vector<float>* extra_bias = nullptr,
-                        bool want_bias = true) {
-    auto it = packed.find(key);
+                        bool want_bias = true, const std::string& cache_suffix = "") {
+    auto it = packed.find(key + cache_suffix);
     if (it != packed.end()) return it->second;
     const HostT& w = T(key + ".weight");
     GP_REQUIRE(w.shape.size() == 4, key + ": conv weight must be 4-D");
@@ -204,7 +204,7 @@ struct gp_engine {
     }
     if (extra_bias)
       for (int i = 0; i < cout; ++i) bias[i] += (*extra_bias)[i];
-    return packed.emplace(key, pack({segs}, cout, bias)).first->second;
+    return packed.emplace(key + cache_suffix, pack({segs}, cout, bias)).first->second;
   }
 
   // nearest-2x upsample followed by 3x3 conv == four parity-specific 2x2 convs on the source grid
@@ -631,16 +631,37 @@ struct gp_engine {
         cur = y;
       }
       if (i < 3) {
-        // Upsample2D: nearest x2 (to the skip's size when H/8 is odd) + 3x3 conv, fused.  Only the
-        // exact-2x case is supported by the fused kernel (all BASELINE configs are multiples of 64).
-        const T4& nxt = skips.back();
-        GP_REQUIRE(nxt.H == 2 * cur.H && nxt.W == 2 * cur.W, "input height/width must be multiples of 64");
+        // Upsample2D: nearest resize to the skip's size + 3x3 conv.  Exact 2x (every level, when H and W are
+        // multiples of 64): the fused four-class 2x2 form.  Otherwise (a level with an odd extent: the target is
+        // 2n-1, diffusers' `upsample_size`) the resized tensor is materialised and the plain 3x3 weights are used —
+        // the pre-summed 2x2 weights would be wrong in the last row / column, where the padding cuts the window.
+        const T4 nxt = skips.back();
         const std::string k = u + ".up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
-        T4 y = b.alloc(cur.N, 2 * cur.H, 2 * cur.W, cur.C);
-        ConvArgs c; c.srcs = {cur}; c.mode = 3; c.w = &conv_up_w(k); c.out = y; c.want_stats = true;
-        b.conv(k, c);
-        b.release(cur);
-        cur = y;
+        const PackedW& plain = conv_w(k, {cur.C}, "", {}, nullptr, true, "#plain");   // packed at finalize for both paths
+        if (nxt.H == 2 * cur.H && nxt.W == 2 * cur.W) {
+          T4 y = b.alloc(cur.N, 2 * cur.H, 2 * cur.W, cur.C);
+          ConvArgs c; c.srcs = {cur}; c.mode = 3; c.w = &conv_up_w(k); c.out = y; c.want_stats = true;
+          b.conv(k, c);
+          b.release(cur);
+          cur = y;
+        } else {
+          GP_REQUIRE(nxt.H <= 2 * cur.H && nxt.H >= 2 * cur.H - 1 && nxt.W <= 2 * cur.W && nxt.W >= 2 * cur.W - 1,
+                     "unexpected skip size in the UNet up path");
+          T4 up = b.alloc(cur.N, nxt.H, nxt.W, cur.C);
+          if (!b.measuring()) {
+            const void* src = b.ptr(cur);
+            void* dst = b.ptr(up);
+            const int n = cur.N, h = cur.H, w = cur.W, oh = nxt.H, ow = nxt.W, ch = cur.C;
+            b.custom(k + ".nearest", 1, (double)cur.bytes() + (double)up.bytes(),
+                     [=](cudaStream_t s) { return nearest_resize(src, dst, n, h, w, oh, ow, ch, s); });
+          }
+          b.release(cur);
+          T4 y = b.alloc(up.N, up.H, up.W, up.C);
+          ConvArgs c; c.srcs = {up}; c.mode = 0; c.w = &plain; c.out = y; c.want_stats = true;
+          b.conv(k, c);
+          b.release(up);
+          cur = y;
+        }
       }
       if (want_feats) {
         // custom_unet.py:400 taps each up block's output (after its upsampler); keep them alive
@@ -809,7 +830,12 @@ struct gp_engine {
   std::unordered_map<std::string, std::vector<float>> folded;   // host fp32 folded weights (live until packed)
 
   void build(Builder& b, Plan* plan, int B, int H, int W) {
-    GP_REQUIRE(H % 64 == 0 && W % 64 == 0, "this build supports H, W multiples of 64");
+    // The VAE needs multiples of 8 (three stride-2 stages); the UNet handles odd latent extents like diffusers
+    // (ceil on the way down, resize to the skip's size on the way up).  The DPT head's fusion stages assume
+    // matching pyramid sizes: multiples of 64 there (the reference resizes the skip bilinearly otherwise).
+    if (cfg.readout == GP_READOUT_DPT)
+      GP_REQUIRE(H % 64 == 0 && W % 64 == 0, "the DPT readout supports H, W multiples of 64");
+    GP_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of 8 (AutoencoderKL)");
     // persistent buffers first so their offsets are identical in both passes
     const size_t in_off = b.raw_alloc((size_t)B * 3 * H * W * 4);
     const size_t out_off = b.raw_alloc((size_t)B * 3 * H * W * 4);

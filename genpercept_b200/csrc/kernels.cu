@@ -726,4 +726,30 @@ cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratc
   return cudaGetLastError();
 }
 
+namespace {
+__global__ void nearest_resize_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int OH,
+                                      int OW, int nvec, float sy, float sx, long long total_vec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long r = i / nvec;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int iy = min((int)floorf(oy * sy), H - 1), ix = min((int)floorf(ox * sx), W - 1);   // ATen nearest index
+    out[i] = __ldg(in + (((long long)n * H + iy) * W + ix) * nvec + v);
+  }
+}
+}  // namespace
+
+cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const long long total_vec = (long long)N * OH * OW * (C / 8);
+  nearest_resize_kernel<<<blocks_for(total_vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in),
+                                                                  reinterpret_cast<uint4*>(out), N, H, W, OH, OW, C / 8,
+                                                                  (float)H / (float)OH, (float)W / (float)OW, total_vec);
+  return cudaGetLastError();
+}
+
 }  // namespace gp

@@ -53,6 +53,9 @@ cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16
 cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s);
 cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16,
                           cudaStream_t s);
+// F.interpolate(size=(OH,OW), mode="nearest") on 16-bit NHWC: src = min(floor(dst * in/out), in-1)  (the UNet's
+// Upsample2D with an explicit output size, when H/8 or W/8 is not a multiple of 8)
+cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s);
 // u8 / f16 / f32 NCHW [N,3,H,W] -> 16-bit NHWC8 (channels 3..7 zero); u8 is mapped x/255*2-1.
 cudaError_t preprocess_rgb(const void* in, int in_kind /*0 u8, 1 f16, 2 f32*/, void* out, int N, int H,
                            int W, bool bf16, cudaStream_t s);

@@ -127,3 +127,27 @@ def test_error_not_worse_than_the_reference_fp16_path(engines, synth_state, text
               f"engine vs fp32 max {e_ours.max():.3e} mean {e_ours.mean():.3e}")
         assert e_ours.mean() <= 1.25 * e_ref.mean() + 1e-4
         assert e_ours.max() <= 1.25 * e_ref.max() + 1e-3
+
+
+@pytest.mark.parametrize("hw", [(72, 88), (104, 64), (64, 120)])
+def test_sizes_that_are_multiples_of_8_only(engines, synth_state, text_embed, hw):
+    """H/8 or W/8 odd at some UNet level: diffusers' `upsample_size` path (resize to the skip's 2n-1 extent, then the
+    plain 3x3 conv) — e.g. the 432x768 a 16:9 image becomes at the default processing resolution."""
+    from oracle.pipeline import OraclePipeline
+    H, W = hw
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    rgb = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8)
+    e = engines["vae"]
+    depth = e.infer(rgb.cuda(), out_channels=1).cpu().numpy()
+    normal = e.infer(rgb.cuda(), out_channels=3).cpu().numpy()
+    p = OraclePipeline(synth_state, text_embed)
+    x = rgb.float() / 255.0 * 2.0 - 1.0
+    ref_d = p.single_infer(x, mode="depth").numpy()
+    ref_n = p.single_infer(x, mode="normal").numpy()
+    assert depth.shape == (2, 1, H, W) and normal.shape == (2, 3, H, W)
+    assert _report(f"depth {H}x{W}", depth, ref_d) < TOL["out"]
+    assert _report(f"normal {H}x{W}", normal, ref_n) < TOL["out"]
+    with pytest.raises(RuntimeError):
+        e.infer(torch.zeros((1, 3, 68, 64), dtype=torch.uint8, device="cuda"))      # not a multiple of 8
+    with pytest.raises(RuntimeError):
+        engines["dpt"].infer(torch.zeros((1, 3, 72, 64), dtype=torch.uint8, device="cuda"))   # DPT readout: 64 only
