@@ -329,6 +329,59 @@ struct gp_engine {
     return xattns.emplace(blk, x).first->second;
   }
 
+  // General cross-attention over a constant n-token context (non-empty prompts).  Both projections of
+  // the context are constants of the pipeline, so per head h
+  //     scores_h = LN(x) A_h,   A_h = Wq_h^T K_h^T / sqrt(d)   ([C] -> [n]),   K = ctx Wk^T
+  //     out     += P_h B_h,     B_h = V_h Wo_h^T               ([n] -> [C]),   V = ctx Wv^T
+  // i.e. two 1x1 GEMMs ([C] -> [heads*n] and back, columns padded to a multiple of 64) around a per-head softmax.
+  struct XattnGen { const PackedW* A; const PackedW* B; int Kp; };
+  std::unordered_map<std::string, XattnGen> xattn_gens;
+  const XattnGen& xattn_general_w(const std::string& blk, int C, int heads) {
+    auto it = xattn_gens.find(blk);
+    if (it != xattn_gens.end()) return it->second;
+    const int n = n_tokens, d = C / heads;
+    const int Kp = (heads * n + 63) / 64 * 64;
+    XattnGen xg;
+    xg.Kp = Kp;
+    if (!packed.count(blk + ".attn2.A")) {
+      const HostT &wq = T(blk + ".attn2.to_q.weight"), &wk = T(blk + ".attn2.to_k.weight"), &wv = T(blk + ".attn2.to_v.weight");
+      const HostT &wo = T(blk + ".attn2.to_out.0.weight"), &bo = T(blk + ".attn2.to_out.0.bias");
+      const int E = (int)wk.shape[1];
+      std::vector<float> K((size_t)n * C), V((size_t)n * C);
+      for (int t = 0; t < n; ++t)
+        for (int c = 0; c < C; ++c) {
+          double sk = 0, sv = 0;
+          const float* te = &text_embed[(size_t)t * E];
+          const float *rk = &wk.d[(size_t)c * E], *rv = &wv.d[(size_t)c * E];
+          for (int e = 0; e < E; ++e) { sk += (double)te[e] * rk[e]; sv += (double)te[e] * rv[e]; }
+          K[(size_t)t * C + c] = (float)sk; V[(size_t)t * C + c] = (float)sv;
+        }
+      const double scale = 1.0 / std::sqrt((double)d);
+      std::vector<float> A((size_t)Kp * C, 0.f), Bm((size_t)C * Kp, 0.f);
+      for (int h = 0; h < heads; ++h)
+        for (int j = 0; j < n; ++j) {
+          float* row = &A[(size_t)(h * n + j) * C];
+          for (int dd = 0; dd < d; ++dd) {
+            const float kv = (float)(K[(size_t)j * C + h * d + dd] * scale);
+            const float* wr = &wq.d[(size_t)(h * d + dd) * C];
+            for (int ci = 0; ci < C; ++ci) row[ci] += wr[ci] * kv;
+          }
+          for (int co = 0; co < C; ++co) {
+            double s = 0;
+            const float* wr = &wo.d[(size_t)co * C + h * d];
+            const float* vr = &V[(size_t)j * C + h * d];
+            for (int dd = 0; dd < d; ++dd) s += (double)wr[dd] * vr[dd];
+            Bm[(size_t)co * Kp + h * n + j] = (float)s;
+          }
+        }
+      mat_w(blk + ".attn2.A", Kp, C, A.data(), {});
+      mat_w(blk + ".attn2.B", C, Kp, Bm.data(), bo.d);
+    }
+    xg.A = &packed.at(blk + ".attn2.A");
+    xg.B = &packed.at(blk + ".attn2.B");
+    return xattn_gens.emplace(blk, xg).first->second;
+  }
+
   void compute_temb() {
     if (!temb.empty()) return;
     const HostT &w1 = T("unet.time_embedding.linear_1.weight"), &b1 = T("unet.time_embedding.linear_1.bias");
@@ -453,7 +506,26 @@ struct gp_engine {
     b.release(t);
     // cross attention (2-token closed form, fused with its LayerNorm and residual)
     T4 t2 = b.alloc(x.N, x.H, x.W, C);
-    b.xattn(blk + ".attn2", t1, xattn_w(blk, C, heads), 1e-5f, t2);
+    if (n_tokens == 2) {
+      b.xattn(blk + ".attn2", t1, xattn_w(blk, C, heads), 1e-5f, t2);
+    } else {   // general context length: LN -> [C -> heads*n] GEMM -> per-head softmax -> [heads*n -> C] GEMM + residual
+      const XattnGen& xg = xattn_general_w(blk, C, heads);
+      T4 l2 = b.alloc(x.N, x.H, x.W, C);
+      b.ln(blk + ".norm2", t1, norm_w(blk + ".norm2"), 1e-5f, l2);
+      T4 sc = b.alloc(x.N, x.H, x.W, xg.Kp);
+      { ConvArgs c; c.srcs = {l2}; c.ks = 1; c.w = xg.A; c.out = sc; b.conv(blk + ".attn2.scores", c); }
+      b.release(l2);
+      if (!b.measuring()) {
+        void* sp = b.ptr(sc);
+        const long long rows = (long long)x.N * x.H * x.W;
+        const int kp = xg.Kp, nh = heads, nt = n_tokens;
+        const bool bf = bf16;
+        b.custom(blk + ".attn2.softmax", 1, 2.0 * rows * kp * 2,
+                 [=](cudaStream_t s) { return softmax_groups(sp, rows, kp, nh, nt, bf, s); });
+      }
+      { ConvArgs c; c.srcs = {sc}; c.ks = 1; c.w = xg.B; c.out = t2; c.res1 = &t1; b.conv(blk + ".attn2.out", c); }
+      b.release(sc);
+    }
     b.release(t1);
     // feed-forward (GEGLU)
     T4 l3 = b.alloc(x.N, x.H, x.W, C);

@@ -743,6 +743,33 @@ __global__ void nearest_resize_kernel(const uint4* __restrict__ in, uint4* __res
 }
 }  // namespace
 
+namespace {
+template <bool BF16>
+__global__ void softmax_groups_kernel(uint16_t* __restrict__ x, long long rows, int ld, int groups, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * groups) return;
+  uint16_t* p = x + (i / groups) * ld + (i % groups) * n;
+  auto ld16 = [](uint16_t v) { return BF16 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v)); };
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, ld16(p[j]));
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += __expf(ld16(p[j]) - m);
+  const float inv = 1.f / s;
+  for (int j = 0; j < n; ++j) {
+    const float v = __expf(ld16(p[j]) - m) * inv;
+    p[j] = BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  }
+}
+}  // namespace
+
+cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s) {
+  if (groups < 1 || n < 1 || groups * n > ld) return cudaErrorInvalidValue;
+  const long long total = rows * groups;
+  GP_DISPATCH_BF16(bf16, (softmax_groups_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+                             reinterpret_cast<uint16_t*>(x), rows, ld, groups, n)));
+  return cudaGetLastError();
+}
+
 cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   const long long total_vec = (long long)N * OH * OW * (C / 8);

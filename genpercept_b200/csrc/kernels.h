@@ -53,6 +53,9 @@ cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16
 cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s);
 cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16,
                           cudaStream_t s);
+// In-place softmax over each of `groups` consecutive runs of `n` columns of every row of x [rows, ld] (16-bit); columns
+// beyond groups*n are left untouched (zero padding of the general cross-attention score matrix).
+cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s);
 // F.interpolate(size=(OH,OW), mode="nearest") on 16-bit NHWC: src = min(floor(dst * in/out), in-1)  (the UNet's
 // Upsample2D with an explicit output size, when H/8 or W/8 is not a multiple of 8)
 cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s);

@@ -151,3 +151,28 @@ def test_sizes_that_are_multiples_of_8_only(engines, synth_state, text_embed, hw
         e.infer(torch.zeros((1, 3, 68, 64), dtype=torch.uint8, device="cuda"))      # not a multiple of 8
     with pytest.raises(RuntimeError):
         engines["dpt"].infer(torch.zeros((1, 3, 72, 64), dtype=torch.uint8, device="cuda"))   # DPT readout: 64 only
+
+
+@pytest.mark.parametrize("ntok", [1, 5, 13])
+def test_general_context_length(synth_state, text_embed, ntok):
+    """Non-empty prompts: an n-token context takes the general cross-attention path (two 1x1 GEMMs
+    around a per-head softmax) instead of the 2-token closed form; compared with the oracle's SDPA."""
+    from genpercept_b200.engine import Engine
+    from oracle.pipeline import OraclePipeline
+    g = torch.Generator().manual_seed(100 + ntok)
+    te = torch.randn((1, ntok, 1024), generator=g) * float(text_embed.float().std())
+    e = Engine(dtype=torch.float16, readout="vae")
+    try:
+        e.load_state("unet", synth_state["unet"])
+        e.load_state("vae", synth_state["vae"])
+        e.set_text_embed(te)
+        e.finalize()
+        rgb = torch.randint(0, 256, (2, 3, 64, 64), generator=g, dtype=torch.uint8)
+        depth = e.infer(rgb.cuda(), out_channels=1).cpu().numpy()
+    finally:
+        e.close()
+    ref = OraclePipeline(synth_state, te).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
+    assert _report(f"depth, {ntok}-token context", depth, ref) < TOL["out"]
+    # the context matters: the 2-token empty-prompt result is a different map
+    ref2 = OraclePipeline(synth_state, text_embed).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
+    print("   |oracle(n tokens) - oracle(empty prompt)| max", float(np.abs(ref - ref2).max()))
