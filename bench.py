@@ -193,7 +193,8 @@ def main():
     state = W.synth_state(1234, with_dpt=args.readout == "dpt")
     pipe = GenPerceptPipeline(unet=state["unet"], vae=state["vae"],
                               customized_head=state["dpt"] if args.readout == "dpt" else None,
-                              text_embed=text_embed(), torch_dtype=dt, device=local, cuda_graph=args.cuda_graph)
+                              text_embed=text_embed(), torch_dtype=dt, device=local,
+                              cuda_graph=True if args.cuda_graph else ("auto" if args.batch * args.res * args.res <= 2 * 768 * 768 else False))
     eng = pipe._engine
     B, R = args.batch, args.res
     g = torch.Generator().manual_seed(1002 + rank)
@@ -301,7 +302,7 @@ def main():
                        "global_batch": world * B, "parallelism": f"dp{world} (independent replicas, batch sharded)",
                        "l2": f"no flush needed: per-step working set {info['arena_bytes'] / 2**30:.1f} GiB arena + "
                              f"{info['weight_bytes'] / 2**30:.2f} GiB weights >> 126 MB L2; 2 alternating inputs",
-                       "algorithmic_tflop_per_image": per_img / 1e12, "cuda_graph": bool(args.cuda_graph)},
+                       "algorithmic_tflop_per_image": per_img / 1e12, "cuda_graph": bool(args.cuda_graph) or args.batch * args.res * args.res <= 2 * 768 * 768},
             "model_tflops": n_img * per_img / (ms_dev / 1000.0) / 1e12,
             "e2e": {"value": n_img / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": B * 3 * R * R,
                     "d2h_bytes_per_step": B * R * R * 4, "ms_per_step": ms_e2e / args.steps,

@@ -92,7 +92,7 @@ def _check_free(st, what):
 class Engine:
     """One engine per (process, GPU).  Mirrors the C-ABI one to one."""
 
-    def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph=False):
+    def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("genpercept_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.L = lib()
@@ -100,7 +100,7 @@ class Engine:
         self.readout = readout
         self.device = torch.device("cuda", device)
         cfg = _Config(device, _gp_dtype(dtype), GP_READOUT_DPT if readout == "dpt" else GP_READOUT_VAE, timestep,
-                      1 if cuda_graph else 0)
+                      2 if cuda_graph == "auto" else (1 if cuda_graph else 0))   # auto: graphs for small plans
         self.h = c_void_p()
         st = self.L.gp_create(byref(cfg), byref(self.h))
         if st != 0:

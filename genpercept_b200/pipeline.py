@@ -74,7 +74,7 @@ class GenPerceptPipeline:
     def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None,
                  default_denoising_steps: Optional[int] = 10, default_processing_resolution: Optional[int] = 768,
                  rgb_blending=False, customized_head=None, genpercept_pipeline=True, *, text_embed=None,
-                 torch_dtype=torch.float16, device=0, cuda_graph=False, fix_timesteps=None):
+                 torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None):
         self.genpercept_pipeline = genpercept_pipeline
         if not genpercept_pipeline:
             raise NotImplementedError("only the one-step GenPercept mode (genpercept_pipeline=True) is built; "

@@ -43,7 +43,7 @@ typedef struct {
   int readout;           /* gp_readout: VAE decoder (run.py default) or DPT head (:296-301)  */
   int timestep;          /* UNet timestep; 1 for GenPercept (ddim.py + scheduler beta=1), or
                             the reference's --fix_timesteps value                           */
-  int use_cuda_graph;    /* capture the planned op list into one CUDA graph                  */
+  int use_cuda_graph;    /* 0 eager, 1 replay one captured CUDA graph per plan, 2 auto (small plans) */
 } gp_config;
 
 /* replaces: GenPerceptPipeline.__init__/from_pretrained model assembly (run.py:314-376) */
@@ -56,7 +56,9 @@ const char* gp_last_error(gp_engine* e);
 gp_status gp_load_tensor(gp_engine* e, const char* key, const void* host_ptr, int dtype,
                          const int64_t* shape, int ndim);
 /* replaces: encode_text()'s cached self.text_embed (genpercept_pipeline.py:360-372, :425-429).
- * fp32 [n_tokens, dim]; the engine's closed-form cross-attention requires n_tokens == 2. */
+ * fp32 [n_tokens, 1024].  n_tokens == 2 (the empty prompt) takes the closed-form cross-attention; any other
+ * length the general one (context projections folded into two 1x1 GEMMs around a per-head softmax).  The
+ * context is a constant of the engine from gp_finalize on, like the reference's cached self.text_embed. */
 gp_status gp_set_text_embed(gp_engine* e, const float* host_ptr, int n_tokens, int dim);
 /* folds constants, re-packs weights K-major 16-bit, uploads. */
 gp_status gp_finalize(gp_engine* e);
