@@ -126,6 +126,9 @@ gp_status gp_quantize(const float* pred, int pred_on_host, size_t n, int bits, v
 /* time one igemm configuration: returns average microseconds over `iters` launches */
 gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int ks, int mode, int iters,
                         double* usec, double* flops);
+/* debug (scripts/fattn_trace.py): a device buffer of >= 1024 int64 that CTA 0 of the fused-attention launches planned
+ * afterwards fills with clock64() stamps at its phase boundaries; NULL switches the stamps off again. */
+void gp_debug_fattn_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }
