@@ -57,3 +57,13 @@ def test_colorize_and_quantize():
     q = np.array([0.0, 0.5, 1.0, 0.9999], np.float32)
     assert IP.quantize(q, 8).tolist() == [0, 127, 255, 254]
     assert IP.quantize(q, 16).tolist() == [0, 32767, 65535, 65528]
+
+
+def test_resize_matches_the_committed_torchvision_golden(golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "resize_torchvision.npz"))
+    for mode in ("bilinear", "bicubic"):
+        for oh, ow in ((27, 36), (96, 130)):
+            d = np.abs(g[f"u8_{mode}_{oh}x{ow}"].astype(np.int32) - IP.resize_aa(g["x"], oh, ow, mode).astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+            assert np.abs(g[f"f32_{mode}_{oh}x{ow}"] - IP.resize_aa(g["f"], oh, ow, mode)).max() < 5e-6
