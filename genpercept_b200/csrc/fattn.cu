@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
           const float x = __uint_as_float(s[c][q]) * c2 - mb;      // <= thr
           pv[q] = (POLY && (q & 3) == 3) ? ex2_fma(x) : ex2(x);
         }
+        // hand the MUFU to the other tile once the exponentials of chunk `pp_early` are issued: its wake-up latency
+        // and the first FFMAs of its pass run under this tile's remaining sums / packs / stores
+        if (pingpong && c == p.pp_early) mbar_arrive(&pp[1 - t]);
 #pragma unroll
         for (int q = 0; q < 32; q += 8) {
           l0 += pv[q]; l1 += pv[q + 1]; l2 += pv[q + 2]; l3 += pv[q + 3];
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
                        pack16<BF16>(pv[8 * i + 6], pv[8 * i + 7]));
       }
       l += ((l0 + l1) + (l2 + l3)) + ((l4 + l5) + (l6 + l7));
-      if (pingpong) mbar_arrive(&pp[1 - t]);
+      if (pingpong && p.pp_early >= 4) mbar_arrive(&pp[1 - t]);
       if (tr && j < 64) p.trace[j * 8 + 5] = clock64();
       tc_fence_before();                          // the O_t rescale (if any) is ordered before the next P.V
       fence_proxy_async_smem();                   // P_t visible to the tensor core (async proxy)
@@ -368,7 +371,7 @@ long long* fattn_get_trace() { return g_trace; }
 cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
   static bool attr_set = false;
   static bool poly = false;
-  static int stagger = 0, pingpong = 1;
+  static int stagger = 0, pingpong = 1, pp_early = 1;   // r1l trace: period 3560 (4) / 3350 (3) / 3290 (2) / 3180 (1) / 3440 (0)
   if (!attr_set) {
     const void* fns[4] = {(const void*)fattn_kernel<false, false>, (const void*)fattn_kernel<false, true>,
                           (const void*)fattn_kernel<true, false>, (const void*)fattn_kernel<true, true>};
@@ -382,11 +385,14 @@ cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
     if (env) stagger = atoi(env);
     env = getenv("GP_FATTN_PP");                 // 0: let the exponential passes of the two tiles overlap (A/B switch)
     if (env && env[0] == '0') pingpong = 0;
+    env = getenv("GP_FATTN_PP_EARLY");           // 0..3: hand over after that 32-column chunk's exponentials; 4: after the pass
+    if (env) pp_early = atoi(env);
     attr_set = true;
   }
   FattnParams p = p_in;
   p.stagger = stagger;
   p.pingpong = pingpong;
+  p.pp_early = pp_early;
   const int grid = p.B * p.heads * ((p.q_tiles + 1) / 2);
   if (grid <= 0) return cudaSuccess;
   if (p.bf16) {
