@@ -176,3 +176,41 @@ def test_general_context_length(synth_state, text_embed, ntok):
     # the context matters: the 2-token empty-prompt result is a different map
     ref2 = OraclePipeline(synth_state, text_embed).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
     print("   |oracle(n tokens) - oracle(empty prompt)| max", float(np.abs(ref - ref2).max()))
+
+
+def test_mid_size_against_the_oracle(engines, synth_state, text_embed):
+    """256x384, batch 2: the largest size the CPU oracle finishes in seconds; exercises the patch-resident conv
+    loop (W % 128 == 0), multi-block attention (T = 1536) and the TMA residual path with full tiles."""
+    from oracle.pipeline import OraclePipeline
+    g = torch.Generator().manual_seed(256384)
+    rgb = torch.randint(0, 256, (2, 3, 256, 384), generator=g, dtype=torch.uint8)
+    depth = engines["vae"].infer(rgb.cuda(), out_channels=1).cpu().numpy()
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    ref = OraclePipeline(synth_state, text_embed).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
+    assert _report("depth 256x384", depth, ref) < TOL["out"]
+
+
+def test_full_size_properties(engines):
+    """BASELINE.json configs[1] shape (8 x 768 x 768), where the oracle would take minutes: size-independent
+    properties of the path instead — run-to-run bits, host I/O == device I/O, batch permutation equivariance
+    (images are independent), output range, and the DPT readout's per-image min-max."""
+    e = engines["vae"]
+    g = torch.Generator().manual_seed(768)
+    base = torch.rand((8, 3, 12, 12), generator=g)
+    rgb = (torch.nn.functional.interpolate(base, size=(768, 768), mode="bicubic").clamp(0, 1) * 255).to(torch.uint8)
+    a = e.infer(rgb.cuda(), out_channels=1).cpu()
+    b = e.infer(rgb.cuda(), out_channels=1).cpu()
+    assert torch.equal(a, b)
+    host_out = torch.empty((8, 1, 768, 768), dtype=torch.float32).pin_memory()
+    assert torch.equal(e.infer(rgb.pin_memory(), out_channels=1, out=host_out), a)
+    assert a.min() >= 0 and a.max() <= 1 and a.std() > 1e-3
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
+    c = e.infer(rgb[perm].cuda(), out_channels=1).cpu()
+    d = (c - a[perm]).abs().max().item()
+    print(f"768x768 batch-8 permutation: max|delta| = {d:.3e}")
+    assert d < 6e-3
+    n3 = e.infer(rgb[:2].cuda(), out_channels=3).cpu()
+    assert n3.shape == (2, 3, 768, 768) and n3.min() >= 0 and n3.max() <= 1
+    dd = engines["dpt"].infer(rgb[:2].cuda()).cpu()
+    for i in range(2):
+        assert dd[i].min().item() == 0.0 and dd[i].max().item() == 1.0
