@@ -305,16 +305,18 @@ __global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long ro
   for (int i = lane; i < T; i += 32) row[i] = f32_to_f16<BF16>(__expf(f16_to_f32<BF16>(row[i]) - m) * inv);
 }
 
-template <bool BF16>
+// MV = 8-column vectors per thread: 8 (any T up to 16384, 256 threads) or 3 with 512 threads for T <= 12288 — the
+// VAE mid-block rows (T = 9216) then hold 24 values per thread instead of 64 (r1_final: 2.5 TB/s at low occupancy).
+template <bool BF16, int MV>
 __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
   __shared__ float red[32];
   uint16_t* row = s + (long long)blockIdx.x * Tp;
   const int nvec = T / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float f[kSmMaxVec][8];
+  float f[MV][8];
   float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < kSmMaxVec; ++i) {
+  for (int i = 0; i < MV; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
       unpack8<BF16>(*reinterpret_cast<const uint4*>(row + v * 8), f[i]);
@@ -330,7 +332,7 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
   __syncthreads();
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSmMaxVec; ++i) {
+  for (int i = 0; i < MV; ++i) {
     if (threadIdx.x + i * blockDim.x < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { f[i][e] = __expf(f[i][e] - m); sum += f[i][e]; }
@@ -343,7 +345,7 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
   for (int w = 0; w < nwarp; ++w) sum += red[w];
   const float inv = 1.f / sum;
 #pragma unroll
-  for (int i = 0; i < kSmMaxVec; ++i) {
+  for (int i = 0; i < MV; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
 #pragma unroll
@@ -667,7 +669,11 @@ cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cu
   int threads = ((T / 8 + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
-  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
+  if (T / 8 > 256 && T / 8 <= 512 * 3) {
+    GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, 3><<<(unsigned)rows, 512, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
+    return cudaGetLastError();
+  }
+  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, kSmMaxVec><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
   return cudaGetLastError();
 }
 

@@ -113,7 +113,10 @@ gp_status gp_bilinear_up2x(int dtype, const void* x, int N, int H, int W, int C,
  * as called by resize_max_res (/root/reference/genpercept/util/image_util.py:75-105) and by the resize back
  * to the input resolution (/root/reference/genpercept/genpercept_pipeline.py:301-307): N planes [N,H,W] ->
  * [N,OH,OW]; src GP_U8 or GP_F32; dst GP_F32, or GP_U8 = round-half-even (+ clamp for bicubic) as torchvision
- * does for integer tensors; mode 0 bilinear, 1 bicubic. */
+ * does for integer tensors; mode 0 bilinear, 1 bicubic.
+ * The three pre/post entry points share one growing scratch buffer and the cached filter tables per device:
+ * like gp_infer on one engine they are meant for one caller thread and stream-ordered use (calls on the same
+ * stream, or separated by a synchronisation); they return after the copy whenever a host buffer is involved. */
 gp_status gp_resize_aa(const void* src, int src_dtype, int src_on_host, int N, int H, int W, void* dst, int dst_dtype,
                        int dst_on_host, int OH, int OW, int mode, void* stream);
 /* colorize_depth_maps + the uint8 cast at its call site (image_util.py:25-63, genpercept_pipeline.py:318-321):
