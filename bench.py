@@ -124,7 +124,8 @@ def cpu_baseline_sample(state, res, threads, steps=1, warmup=0):
     (seconds per step, threads used)."""
     from oracle.pipeline import OraclePipeline
     p = OraclePipeline(state, text_embed())
-    threads = best_thread_count(p, threads)
+    fixed = os.environ.get("GP_BENCH_CPU_THREADS")            # skip the probe (tests)
+    threads = min(int(fixed), threads) if fixed else best_thread_count(p, threads)
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1002)
     x = torch.randint(0, 256, (1, 3, res, res), generator=g, dtype=torch.uint8).float() / 255.0 * 2.0 - 1.0

@@ -12,8 +12,9 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def _run(args, timeout=900):
+    env = dict(os.environ, GP_BENCH_CPU_THREADS="8")          # skip the thread-count probe of the CPU arm
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout,
-                       cwd=ROOT)
+                       cwd=ROOT, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, p.stdout
