@@ -42,3 +42,17 @@ def test_engine_arm_line_on_gpu():
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"])
     assert "workload" in j["config"] and "sm_mhz" in j["clocks"]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """N > 1: the driver launches the reference arm like the engine arm; rank 0 alone works and prints."""
+    env = dict(os.environ, GP_BENCH_CPU_THREADS="8")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0", "--ref-res", "64"], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                       env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0
