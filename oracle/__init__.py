@@ -15,5 +15,6 @@ its arithmetic lives in diffusers which cannot be imported here -> **parity unpi
 VAE/UNet graphs.  What *is* pinned (tests/test_oracle.py): the DPT head against the reference's own
 class (imported from /root/reference through a 2-symbol diffusers shim; fixtures committed under
 tests/golden/), the scheduler collapse against a literal restatement of ddim.py, parameter counts
-against the published model sizes, and the empty-text embedding fixture.
+against the published model sizes, the empty-text embedding fixture, ``blocks.Upsample2D`` bitwise against the copy
+of diffusers' class the reference vendors (dpt_head.py:92-210), and ``imgproc`` against torchvision's own resize.
 """

@@ -3,6 +3,7 @@ published parameter counts, text-embed fixture, committed end-to-end goldens."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from genpercept_b200 import weights as W
@@ -99,3 +100,26 @@ def test_cross_attention_two_token_closed_form(synth_state, text_embed):
         c0 = V[1] @ Wo.T + bo
         out = c0 + torch.sigmoid(x @ U) @ dV
     torch.testing.assert_close(out, ref, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_upsample2d_matches_the_reference_vendored_class():
+    """/root/reference/genpercept/models/dpt_head.py:92-210 vendors diffusers' ``Upsample2D`` — the one block of the
+    UNet / VAE graphs whose source IS in the reference tree.  oracle.blocks.Upsample2D (used by every up block of both
+    graphs) must match it, including the explicit-size path diffusers takes when a level has an odd extent."""
+    import importlib.util
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden                      # installs the 2-symbol diffusers shim
+    make_golden.load_reference_dpt()
+    ref_mod = sys.modules["ref_dpt_head"]
+    from oracle.blocks import Upsample2D
+    torch.manual_seed(3)
+    ref = ref_mod.Upsample2D(24, use_conv=True).eval()
+    mine = Upsample2D(24).eval()
+    mine.conv.load_state_dict(ref.conv.state_dict())
+    x = torch.randn(2, 24, 7, 9)
+    with torch.no_grad():
+        assert torch.equal(mine(x), ref(x))
+        for size in ((13, 17), (14, 18), (13, 18)):
+            assert torch.equal(mine(x, size), ref(x, output_size=size))
