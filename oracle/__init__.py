@@ -13,7 +13,8 @@ reference`` legs may import this package; the product path (``genpercept_b200``)
 PARITY STATUS: the reference holds no tests or golden tensors for this path, and
 its arithmetic lives in diffusers which cannot be imported here -> **parity unpinned** for the inside of the
 diffusers blocks of the VAE/UNet graphs.  Pinned: the orchestration (single_infer / encode_rgb / decode_pred) against
-the reference's OWN pipeline class executed here around this package's modules
+the reference's OWN pipeline class, and the UNet top-level dataflow (skip stack, upsample_size, DPT taps) against the
+reference's OWN CustomUNet2DConditionModel.forward, both executed here around this package's modules
 (tests/test_oracle_vs_reference_pipeline.py), and (tests/test_oracle.py): the DPT head against the reference's own
 class (imported from /root/reference through a 2-symbol diffusers shim; fixtures committed under
 tests/golden/), the scheduler collapse against a literal restatement of ddim.py, parameter counts

@@ -134,3 +134,91 @@ def test_single_infer_glue_matches_the_reference(ref_pipeline_cls, synth_state, 
         ref = rd.single_infer(rgb, 1, None, False)
     mine = od.single_infer(rgb, mode="depth")
     assert ref.shape == mine.shape and torch.allclose(ref, mine, atol=2e-6, rtol=0), float((ref - mine).abs().max())
+
+
+def _install_unet_shims():
+    import torch.nn as nn
+    _install_shims()
+    d = sys.modules["diffusers"]
+    d.UNet2DConditionModel = type("UNet2DConditionModel", (nn.Module,), {})
+    du = sys.modules["diffusers.utils"]
+    du.deprecate = lambda *a, **k: None
+    du.logging = types.SimpleNamespace(get_logger=lambda *a, **k: None)
+    du.scale_lora_layers = lambda *a, **k: None
+    du.unscale_lora_layers = lambda *a, **k: None
+    unets = types.ModuleType("diffusers.models.unets")
+    u2d = types.ModuleType("diffusers.models.unets.unet_2d_condition")
+    u2d.UNet2DConditionOutput = type("UNet2DConditionOutput", (), {})
+    sys.modules.update({"diffusers.models.unets": unets, "diffusers.models.unets.unet_2d_condition": u2d})
+
+
+def test_unet_dataflow_matches_the_reference_forward(synth_state, text_embed):
+    """/root/reference/genpercept/models/custom_unet.py:34-427 (the reference's own UNet forward: skip stack, the
+    `upsample_size` forwarding for odd extents, the DPT feature taps, conv_norm_out / conv_out) is executed here around
+    the ORACLE's blocks, attached to an instance of the reference class, and compared with oracle.unet's forward."""
+    import torch.nn as nn
+    _install_unet_shims()
+    spec = importlib.util.spec_from_file_location("ref_custom_unet", f"{REF}/genpercept/models/custom_unet.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from oracle.pipeline import OraclePipeline
+    ou = OraclePipeline(synth_state, text_embed).unet
+
+    class Down(nn.Module):
+        def __init__(self, blk, cross):
+            super().__init__()
+            self.blk, self.has_cross_attention = blk, cross
+
+        def forward(self, hidden_states, temb, encoder_hidden_states=None, **kw):
+            return self.blk(hidden_states, temb, encoder_hidden_states)
+
+    class Mid(nn.Module):
+        has_cross_attention = True
+
+        def __init__(self, blk):
+            super().__init__()
+            self.blk = blk
+
+        def forward(self, sample, emb, encoder_hidden_states=None, **kw):
+            return self.blk(sample, emb, encoder_hidden_states)
+
+    class Up(nn.Module):
+        def __init__(self, blk):
+            super().__init__()
+            self.blk, self.has_cross_attention, self.resnets = blk, blk.attentions is not None, blk.resnets
+
+        def forward(self, hidden_states, temb, res_hidden_states_tuple, encoder_hidden_states=None, upsample_size=None, **kw):
+            return self.blk(hidden_states, res_hidden_states_tuple, temb, encoder_hidden_states, upsample_size)
+
+    class TimeEmb(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, t_emb, cond=None):
+            return self.m(t_emb)
+
+    ru = mod.CustomUNet2DConditionModel()
+    ru.num_upsamplers = 3
+    ru.config = types.SimpleNamespace(center_input_sample=False, class_embed_type=None, addition_embed_type=None,
+                                      class_embeddings_concat=False, encoder_hid_dim_type=None)
+    ru.class_embedding = ru.time_embed_act = ru.encoder_hid_proj = None
+    ru.time_proj, ru.time_embedding = ou.time_proj, TimeEmb(ou.time_embedding)
+    ru.conv_in, ru.conv_norm_out, ru.conv_act, ru.conv_out = ou.conv_in, ou.conv_norm_out, nn.SiLU(), ou.conv_out
+    ru.down_blocks = nn.ModuleList([Down(b, i < 3) for i, b in enumerate(ou.down_blocks)])
+    ru.mid_block = Mid(ou.mid_block)
+    ru.up_blocks = nn.ModuleList([Up(b) for b in ou.up_blocks])
+    ru.eval()
+    g = torch.Generator().manual_seed(4)
+    ctx = text_embed.float().reshape(1, -1, 1024)
+    for h, w in ((8, 8), (9, 11), (12, 10)):                    # multiples of 8, odd extents, 8 does not divide
+        x = torch.randn((1, 4, h, w), generator=g)
+        with torch.no_grad():
+            ref = ru(x, 1, ctx)
+            mine = ou(x, torch.tensor([1]), ctx)
+            assert torch.allclose(ref.sample, mine, atol=1e-6, rtol=0), (h, w, float((ref.sample - mine).abs().max()))
+            rf = ru(x, torch.tensor([1]), ctx, return_feature=True).multi_level_feats
+            mf = ou(x, torch.tensor([1]), ctx, return_feature=True)
+            assert len(rf) == len(mf) == 4
+            for a, b in zip(rf, mf):
+                assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=0)
