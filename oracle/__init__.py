@@ -20,4 +20,8 @@ class (imported from /root/reference through a 2-symbol diffusers shim; fixtures
 tests/golden/), the scheduler collapse against a literal restatement of ddim.py, parameter counts
 against the published model sizes, the empty-text embedding fixture, ``blocks.Upsample2D`` bitwise against the copy
 of diffusers' class the reference vendors (dpt_head.py:92-210), and ``imgproc`` against torchvision's own resize.
+Independent cross-check (not the reference): the whole VAE encoder and decoder against the LDM / taming encoder and
+decoder that HF transformers ships (ChameleonVQVAEEncoder, JanusVQVAEDecoder) with the oracle's weights under the LDM
+names — 4e-6 relative (tests/test_oracle_vs_ldm_vae.py).  Still restated only from SURVEY.md App. A: the inside of
+the UNet's ResnetBlock2D (time-embedding add) and Transformer2DModel / BasicTransformerBlock.
 """
