@@ -222,3 +222,36 @@ def test_unet_dataflow_matches_the_reference_forward(synth_state, text_embed):
             assert len(rf) == len(mf) == 4
             for a, b in zip(rf, mf):
                 assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=0)
+
+
+def test_scheduler_constants_match_the_reference_class():
+    """/root/reference/src/customized_modules/ddim.py:144-217 (DDIMSchedulerCustomized.__init__ — the part
+    of the scheduler that IS in the reference tree; set_timesteps / step are diffusers') instantiated from the
+    reference's own hf_configs/scheduler_beta_1.0_1.0/scheduler_config.json, against oracle.scheduler.DDIMOneStep."""
+    import json
+    _install_shims()
+    d = sys.modules["diffusers"]
+    d.DDIMScheduler = getattr(d, "DDIMScheduler", type("DDIMScheduler", (), {}))
+    d.DDPMScheduler = type("DDPMScheduler", (), {})
+    cu = types.ModuleType("diffusers.configuration_utils")
+    cu.ConfigMixin = type("ConfigMixin", (), {})
+    cu.register_to_config = lambda f: f
+    sys.modules["diffusers.configuration_utils"] = cu
+    spec = importlib.util.spec_from_file_location("ref_ddim", f"{REF}/src/customized_modules/ddim.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = json.load(open(f"{REF}/hf_configs/scheduler_beta_1.0_1.0/scheduler_config.json"))
+    kw = {k: v for k, v in cfg.items() if not k.startswith("_") and k != "skip_prk_steps"}
+    ref = mod.DDIMSchedulerCustomized(**kw)
+    from oracle.scheduler import DDIMOneStep
+    mine = DDIMOneStep()
+    assert torch.equal(ref.betas, mine.betas) and torch.equal(ref.alphas_cumprod, mine.alphas_cumprod)
+    assert torch.equal(ref.final_alpha_cumprod, mine.final_alpha_cumprod)
+    assert float(ref.alphas_cumprod[1]) == 0.0 and ref.init_noise_sigma == 1.0       # beta = 1: x_t carries no signal
+    # one DDIM step at the single timestep the pipeline uses (t = 1, leading spacing + offset 1): x0 = -v
+    ts = mine.set_timesteps(1)
+    assert ts.tolist() == [1]
+    g = torch.Generator().manual_seed(0)
+    v, x = torch.randn((1, 4, 8, 8), generator=g), torch.randn((1, 4, 8, 8), generator=g)
+    prev, x0 = mine.step(v, 1, x)
+    assert torch.equal(x0, -v)
