@@ -255,3 +255,29 @@ def test_scheduler_constants_match_the_reference_class():
     v, x = torch.randn((1, 4, 8, 8), generator=g), torch.randn((1, 4, 8, 8), generator=g)
     prev, x0 = mine.step(v, 1, x)
     assert torch.equal(x0, -v)
+
+
+def test_host_image_helpers_match_the_reference_functions():
+    """genpercept_b200.image_util (host mirror) and oracle.imgproc against the reference's own
+    genpercept/util/image_util.py: resize_max_res (:75-105), get_tv_resample_method (:108-119), chw2hwc (:66-72)."""
+    import numpy as np
+    _install_shims()
+    ref = importlib.import_module("genpercept.util.image_util")
+    from genpercept_b200 import image_util as mine
+    from oracle import imgproc as IP
+    g = torch.Generator().manual_seed(8)
+    x = torch.randint(0, 256, (1, 3, 90, 160), generator=g, dtype=torch.uint8)
+    for edge in (64, 128, 200):
+        r = ref.resize_max_res(x, edge)
+        assert torch.equal(mine.resize_max_res(x, edge), r)
+        assert tuple(r.shape[-2:]) == IP.resize_max_res_shape(90, 160, edge)
+        d = np.abs(IP.resize_aa(x.numpy(), *r.shape[-2:]).astype(np.int32) - r.numpy().astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+    for m in ("bilinear", "bicubic", "nearest"):
+        assert mine.get_tv_resample_method(m) == ref.get_tv_resample_method(m)
+    with pytest.raises(ValueError):
+        mine.get_tv_resample_method("lanczos")
+    with pytest.raises(ValueError):
+        ref.get_tv_resample_method("lanczos")
+    c = torch.rand((3, 4, 5), generator=g)
+    assert torch.equal(mine.chw2hwc(c), ref.chw2hwc(c)) and np.array_equal(mine.chw2hwc(c.numpy()), ref.chw2hwc(c.numpy()))
