@@ -56,7 +56,8 @@ void Arena::release(size_t off) {
 }
 
 // ------------------------------------------------------------------------------------ Builder
-Builder::Builder(bool bf16, bool measuring, uint8_t* base) : bf16_(bf16), measuring_(measuring), base_(base) {
+Builder::Builder(bool bf16, bool measuring, uint8_t* base, bool split)
+    : bf16_(bf16), measuring_(measuring), split_(split), base_(base) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
     num_sms = n;
@@ -64,12 +65,14 @@ Builder::Builder(bool bf16, bool measuring, uint8_t* base) : bf16_(bf16), measur
 T4 Builder::alloc(int N, int H, int W, int C) {
   T4 t;
   t.N = N; t.H = H; t.W = W; t.C = C;
+  t.planes = split_ ? 2 : 1;
   t.off = (long long)arena_.alloc(t.bytes());
   return t;
 }
 T4 Builder::external(const void* p, int N, int H, int W, int C) const {
   T4 t;
   t.N = N; t.H = H; t.W = W; t.C = C;
+  t.planes = split_ ? 2 : 1;
   t.off = (long long)(reinterpret_cast<const uint8_t*>(p) - base_);
   return t;
 }
@@ -136,7 +139,10 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   if (a.mode == 1) { Ho = (H + 2 - 3) / 2 + 1; Wo = (W + 2 - 3) / 2 + 1; }
   if (a.mode == 2) { Ho = (H + 1 - 3) / 2 + 1; Wo = (W + 1 - 3) / 2 + 1; }
   if (a.mode == 3) { Ho = 2 * H; Wo = 2 * W; }
-  const int out_c = a.out_f32 ? 0 : a.out.C;
+  const int PL = split_ ? 2 : 1;
+  const int out_cl = a.out_f32 ? 0 : a.out.C;   // logical channels of the 16-bit output ...
+  const int out_c = out_cl * PL;                // ... and its pixel stride in elements
+  GP_REQUIRE(a.w->planes == PL, name + ": packed weights do not match the engine's precision mode");
   const int Cout = a.cout_valid > 0 ? a.cout_valid : a.out.C;
   int cin_total = 0;
   for (auto& s : a.srcs) cin_total += s.C;
@@ -156,15 +162,15 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
-                      (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr &&   // measured slower than the direct GEGLU stores (r1g)
+                      (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr && !split_ &&   // measured slower than the direct GEGLU stores (r1g)
                                    Cout == 2 * a.out.C && (Cout % 128) == 0 && (bn_pre % 128) == 0)
                                 : (Cout == a.out.C && (Cout % 64) == 0 && (bn_pre % 64) == 0));
   // GP_STATS: 0 = never fuse the GroupNorm partial sums into conv epilogues, 1 = always (default), 2 = everywhere
   // except the patch-resident layers (whose main loop runs at the tensor-pipe limit, so the epilogue is critical)
   static const int stats_mode = std::getenv("GP_STATS") ? std::atoi(std::getenv("GP_STATS")) : 1;
   const bool patch_eligible = a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && mt_pre == 2 && (W % 128) == 0 &&
-                              (H % 2) == 0 && std::getenv("GP_NO_PATCH") == nullptr;
-  bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512 && stats_mode != 0 && !(stats_mode == 2 && patch_eligible);
+                              (H % 2) == 0 && !split_ && std::getenv("GP_NO_PATCH") == nullptr;
+  bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512 && stats_mode != 0 && !(stats_mode == 2 && patch_eligible) && !split_;
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
   size_t stats_off = 0;
   const size_t stats_bytes = (size_t)N * num_sms * Cout * 2 * sizeof(float);
@@ -197,9 +203,14 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(s0.C, 64)};
     p.outW = (int)ntok; p.outH = 1;
     p.out_pix_stride = out_c; p.out_row_stride = 0;
-    check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.C, ntok * s0.C, ntok * s0.C, p.TW, 1, bf16_),
+    check_cuda(make_tmap_a(&p.tmA[0], ptr(s0), s0.C, (int)ntok, 1, 1, s0.ps(), ntok * s0.ps(), ntok * s0.ps(), p.TW, 1, bf16_),
                name + ": tmap A");
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    if (split_) {
+      check_cuda(make_tmap_a(&p.tmA[4], reinterpret_cast<const uint16_t*>(ptr(s0)) + s0.C, s0.C, (int)ntok, 1, 1, s0.ps(),
+                             ntok * s0.ps(), ntok * s0.ps(), p.TW, 1, bf16_), name + ": tmap A lo");
+      for (int i = 5; i < 8; ++i) p.tmA[i] = p.tmA[4];
+    }
   } else {
     p.Z1 = N;
     p.a_n_z1 = 1;
@@ -215,27 +226,36 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     int nmap = 0;
     if (a.mode == 0 || a.mode == 3) {
       GP_REQUIRE(a.srcs.size() + a.sc.size() <= 4, name + ": too many sources");
+      auto add_src = [&](const T4& s) {
+        check_cuda(make_tmap_a(&p.tmA[nmap], ptr(s), s.C, W, H, N, s.ps(), (long long)W * s.ps(),
+                               (long long)H * W * s.ps(), p.TW, p.TH, bf16_), name + ": tmap A");
+        if (split_)
+          check_cuda(make_tmap_a(&p.tmA[nmap + 4], reinterpret_cast<const uint16_t*>(ptr(s)) + s.C, s.C, W, H, N, s.ps(),
+                                 (long long)W * s.ps(), (long long)H * W * s.ps(), p.TW, p.TH, bf16_), name + ": tmap A lo");
+        ++nmap;
+      };
       for (auto& s : a.srcs) {
         GP_REQUIRE(s.N == N && s.H == H && s.W == W, name + ": source shape mismatch");
-        check_cuda(make_tmap_a(&p.tmA[nmap++], ptr(s), s.C, W, H, N, s.C, (long long)W * s.C,
-                               (long long)H * W * s.C, p.TW, p.TH, bf16_), name + ": tmap A");
+        add_src(s);
       }
       for (auto& s : a.sc) {
         GP_REQUIRE(s.N == N && s.H == H && s.W == W && a.mode == 0, name + ": shortcut shape mismatch");
-        check_cuda(make_tmap_a(&p.tmA[nmap++], ptr(s), s.C, W, H, N, s.C, (long long)W * s.C,
-                               (long long)H * W * s.C, p.TW, p.TH, bf16_), name + ": tmap A");
+        add_src(s);
       }
     } else {
       GP_REQUIRE(a.srcs.size() == 1 && a.sc.empty() && H >= 2 && W >= 2, name + ": stride-2 needs one source");
       for (int hp = 0; hp < 2; ++hp)
         for (int wp = 0; wp < 2; ++wp) {
-          const uint8_t* b = reinterpret_cast<const uint8_t*>(ptr(s0)) + ((long long)hp * W + wp) * s0.C * 2;
-          check_cuda(make_tmap_a(&p.tmA[hp * 2 + wp], b, s0.C, (W - wp + 1) / 2, (H - hp + 1) / 2, N, 2LL * s0.C,
-                                 2LL * W * s0.C, (long long)H * W * s0.C, p.TW, p.TH, bf16_), name + ": tmap A");
+          const uint8_t* b = reinterpret_cast<const uint8_t*>(ptr(s0)) + ((long long)hp * W + wp) * s0.ps() * 2;
+          check_cuda(make_tmap_a(&p.tmA[hp * 2 + wp], b, s0.C, (W - wp + 1) / 2, (H - hp + 1) / 2, N, 2LL * s0.ps(),
+                                 2LL * W * s0.ps(), (long long)H * W * s0.ps(), p.TW, p.TH, bf16_), name + ": tmap A");
+          if (split_)
+            check_cuda(make_tmap_a(&p.tmA[4 + hp * 2 + wp], b + s0.C * 2, s0.C, (W - wp + 1) / 2, (H - hp + 1) / 2, N, 2LL * s0.ps(),
+                                   2LL * W * s0.ps(), (long long)H * W * s0.ps(), p.TW, p.TH, bf16_), name + ": tmap A lo");
         }
       nmap = 4;
     }
-    for (int i = nmap; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    for (int i = nmap; i < 4; ++i) { p.tmA[i] = p.tmA[0]; if (split_) p.tmA[i + 4] = p.tmA[4]; }
     if (a.mode == 0) {
       int ns = 0;
       const int half = a.ks / 2;
@@ -274,30 +294,40 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
       }
     }
   }
-  check_cuda(make_tmap_b(&p.tmB, a.w->w, a.w->ktot, a.w->rows, a.w->nz, a.w->ktot, (long long)a.w->rows * a.w->ktot,
-                         p.BN, bf16_), name + ": tmap B");
+  check_cuda(make_tmap_b(&p.tmB, a.w->w, (long long)a.w->ktot * PL, a.w->rows, a.w->nz, (long long)a.w->ktot * PL,
+                         (long long)a.w->rows * a.w->ktot * PL, p.BN, bf16_), name + ": tmap B");
+  if (split_) {   // three passes: hi*hi, lo*hi, hi*lo (the weights' lo plane follows the hi plane along K)
+    p.npass = 3;
+    p.pass_amap[0] = 0; p.pass_amap[1] = 4; p.pass_amap[2] = 0;
+    p.pass_bk[0] = 0; p.pass_bk[1] = 0; p.pass_bk[2] = a.w->ktot;
+    if (!a.out_f32) p.out_lo = out_cl;
+  }
   if (staged) {   // output tensor maps for the TMA-store epilogue (one per parity class)
     p.tma_store = 1;
     const int bw = p.TW < 32 ? p.TW : 32, bh = 32 / bw;
-    if (tokens) {
-      const long long ntok = (long long)N * H * W;
-      check_cuda(make_tmap_a(&p.tmOut[0], ptr(a.out), out_c, (int)ntok, 1, 1, out_c, ntok * out_c, ntok * out_c, bw, bh, bf16_),
-                 name + ": tmap out");
-      for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
-    } else if (a.mode == 3) {
-      for (int c = 0; c < 4; ++c) {
-        const int py = c >> 1, px = c & 1;
-        const uint8_t* ob = reinterpret_cast<const uint8_t*>(ptr(a.out)) + ((long long)py * Wo + px) * out_c * 2;
-        check_cuda(make_tmap_a(&p.tmOut[c], ob, out_c, W, H, N, 2LL * out_c, 2LL * Wo * out_c, (long long)Ho * Wo * out_c, bw, bh,
-                               bf16_), name + ": tmap out");
+    for (int pl = 0; pl < PL; ++pl) {          // plane 0: tmOut, plane 1 (high-precision lo): tmOutLo
+      CUtensorMap* tmo = pl == 0 ? p.tmOut : p.tmOutLo;
+      const uint8_t* obase = reinterpret_cast<const uint8_t*>(ptr(a.out)) + (size_t)pl * out_cl * 2;
+      if (tokens) {
+        const long long ntok = (long long)N * H * W;
+        check_cuda(make_tmap_a(&tmo[0], obase, out_cl, (int)ntok, 1, 1, out_c, ntok * out_c, ntok * out_c, bw, bh, bf16_),
+                   name + ": tmap out");
+        for (int i = 1; i < 4; ++i) tmo[i] = tmo[0];
+      } else if (a.mode == 3) {
+        for (int c = 0; c < 4; ++c) {
+          const int py = c >> 1, px = c & 1;
+          const uint8_t* ob = obase + ((long long)py * Wo + px) * out_c * 2;
+          check_cuda(make_tmap_a(&tmo[c], ob, out_cl, W, H, N, 2LL * out_c, 2LL * Wo * out_c, (long long)Ho * Wo * out_c, bw, bh,
+                                 bf16_), name + ": tmap out");
+        }
+      } else {
+        check_cuda(make_tmap_a(&tmo[0], obase, out_cl, Wo, Ho, N, out_c, (long long)Wo * out_c, (long long)Ho * Wo * out_c,
+                               bw, bh, bf16_), name + ": tmap out");
+        for (int i = 1; i < 4; ++i) tmo[i] = tmo[0];
       }
-    } else {
-      check_cuda(make_tmap_a(&p.tmOut[0], ptr(a.out), out_c, Wo, Ho, N, out_c, (long long)Wo * out_c, (long long)Ho * Wo * out_c,
-                             bw, bh, bf16_), name + ": tmap out");
-      for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
     }
     // the residual has the output's shape and addressing: same maps over its base
-    if (a.res1 && !a.res2 && !(a.flags & IG_GEGLU) && std::getenv("GP_NO_RES_TMA") == nullptr) {
+    if (a.res1 && !a.res2 && !(a.flags & IG_GEGLU) && !split_ && std::getenv("GP_NO_RES_TMA") == nullptr) {
       p.res_tma = 1;
       const void* rb = ptr(*a.res1);
       if (tokens) {
@@ -321,7 +351,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   }
   // patch-resident main loop for the wide-image, narrow-N 3x3 layers
   if (staged && a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && p.MT == 2 && p.TW == 128 && p.TH == 2 &&
-      (W % 128) == 0 && (H % 2) == 0 && std::getenv("GP_NO_PATCH") == nullptr) {
+      (W % 128) == 0 && (H % 2) == 0 && !split_ && std::getenv("GP_NO_PATCH") == nullptr) {
     p.patch = 1;
     p.kc_count = ceil_div(s0.C, 64);
     check_cuda(make_tmap_a(&p.tmPatch, ptr(s0), s0.C, W, H, N, s0.C, (long long)W * s0.C, (long long)H * W * s0.C,
@@ -353,11 +383,21 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
 }
 
 void Builder::attention_qkv(const std::string& name, const void* q, const void* k, long long cs, const void* vT, int B,
-                            int T, int heads, int d, const float* pv_bias, const T4& out) {
+                            int T, int heads, int d, const float* pv_bias, const T4& out, long long qk_lo) {
+  // High-precision mode: q / k carry their lo planes `qk_lo` elements further (same pixel stride cs), V^T rows are
+  // [hi Tp | lo Tp], S / P rows likewise; the three GEMM passes of IgemmParams::npass do hi*hi + lo*hi + hi*lo.
   const int Tp = ceil_div(T, 8) * 8;
   const int C = heads * d;
+  const int PL = split_ ? 2 : 1;
+  const long long TpP = (long long)Tp * PL;   // physical row pitch of S and V^T
   static const bool unfused = std::getenv("GP_UNFUSED_ATTN") != nullptr;
-  if (d == 64 && !unfused) {   // fused tcgen05 flash-attention kernel (S and P stay on chip)
+  auto set_passes = [&](IgemmParams& p) {
+    if (!split_) return;
+    p.npass = 3;
+    p.pass_amap[0] = 0; p.pass_amap[1] = 4; p.pass_amap[2] = 0;
+    p.pass_bmap[0] = 0; p.pass_bmap[1] = 0; p.pass_bmap[2] = 1;
+  };
+  if (d == 64 && !unfused && !split_) {   // fused tcgen05 flash-attention kernel (S and P stay on chip)
     if (measuring_) return;
     FattnParams p;
     std::memset(&p, 0, sizeof(p));
@@ -376,7 +416,7 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
     ops.back().kind = 2;
     return;
   }
-  const size_t s_bytes = (size_t)B * heads * T * Tp * 2;
+  const size_t s_bytes = (size_t)B * heads * T * TpP * 2;
   const size_t s_off = arena_.alloc(s_bytes);
   if (!measuring_) {
     void* S = raw_ptr(s_off);
@@ -391,14 +431,23 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       p.nseg[0] = 1;
       p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(d, 64)};
       p.out = S; p.outW = T; p.outH = 1;
-      p.out_pix_stride = Tp; p.out_row_stride = 0;
-      p.out_z1 = (long long)heads * T * Tp; p.out_z0 = (long long)T * Tp;
+      p.out_pix_stride = TpP; p.out_row_stride = 0;
+      p.out_z1 = (long long)heads * T * TpP; p.out_z0 = (long long)T * TpP;
       p.out_sy = p.out_sx = 1;
       p.Cout = T;
       p.BN = choose_bn(T, 0);
       check_cuda(make_tmap_a(&p.tmA[0], q, C, T, 1, B, cs, (long long)T * cs, (long long)T * cs, 128, 1, bf16_), name + ": tmap Q");
       for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
       check_cuda(make_tmap_b(&p.tmB, k, C, T, B, cs, (long long)T * cs, p.BN, bf16_), name + ": tmap K");
+      if (split_) {
+        const uint16_t* ql = reinterpret_cast<const uint16_t*>(q) + qk_lo;
+        const uint16_t* kl = reinterpret_cast<const uint16_t*>(k) + qk_lo;
+        check_cuda(make_tmap_a(&p.tmA[4], ql, C, T, 1, B, cs, (long long)T * cs, (long long)T * cs, 128, 1, bf16_), name + ": tmap Q lo");
+        for (int i = 5; i < 8; ++i) p.tmA[i] = p.tmA[4];
+        check_cuda(make_tmap_b(&p.tmB2, kl, C, T, B, cs, (long long)T * cs, p.BN, bf16_), name + ": tmap K lo");
+        p.out_lo = Tp;
+        set_passes(p);
+      }
       finalize_or_throw(&p, name + ".qk");
       push(name + ".qk", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
            [p](cudaStream_t s) { return igemm_launch(p, s); });
@@ -407,7 +456,8 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
     {
       const long long rows = (long long)B * heads * T;
       const bool bf = bf16_;
-      push(name + ".softmax", 1, 0, 2.0 * s_bytes, [S, rows, T, Tp, bf](cudaStream_t s) { return softmax_rows(S, rows, T, Tp, bf, s); });
+      const bool sp = split_;
+      push(name + ".softmax", 1, 0, 2.0 * s_bytes, [S, rows, T, Tp, bf, sp](cudaStream_t s) { return softmax_rows(S, rows, T, Tp, bf, s, sp); });
     }
     {  // O = P V
       IgemmParams p;
@@ -420,15 +470,24 @@ void Builder::attention_qkv(const std::string& name, const void* q, const void* 
       p.nseg[0] = 1;
       p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(T, 64)};
       p.out = ptr(out); p.outW = T; p.outH = 1;
-      p.out_pix_stride = C; p.out_row_stride = 0;
-      p.out_z1 = (long long)T * C; p.out_z0 = d;
+      p.out_pix_stride = out.ps(); p.out_row_stride = 0;
+      p.out_z1 = (long long)T * out.ps(); p.out_z0 = d;
       p.out_sy = p.out_sx = 1;
       p.Cout = d;
       p.bias = pv_bias;
       p.BN = choose_bn(d, 0);
-      check_cuda(make_tmap_a(&p.tmA[0], S, T, T, 1, B * heads, Tp, (long long)T * Tp, (long long)T * Tp, 128, 1, bf16_), name + ": tmap P");
+      check_cuda(make_tmap_a(&p.tmA[0], S, T, T, 1, B * heads, TpP, (long long)T * TpP, (long long)T * TpP, 128, 1, bf16_), name + ": tmap P");
       for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
-      check_cuda(make_tmap_b(&p.tmB, vT, T, C, B, Tp, (long long)C * Tp, p.BN, bf16_), name + ": tmap Vt");
+      check_cuda(make_tmap_b(&p.tmB, vT, T, C, B, TpP, (long long)C * TpP, p.BN, bf16_), name + ": tmap Vt");
+      if (split_) {
+        check_cuda(make_tmap_a(&p.tmA[4], reinterpret_cast<const uint16_t*>(S) + Tp, T, T, 1, B * heads, TpP, (long long)T * TpP,
+                               (long long)T * TpP, 128, 1, bf16_), name + ": tmap P lo");
+        for (int i = 5; i < 8; ++i) p.tmA[i] = p.tmA[4];
+        check_cuda(make_tmap_b(&p.tmB2, reinterpret_cast<const uint16_t*>(vT) + Tp, T, C, B, TpP, (long long)C * TpP, p.BN, bf16_),
+                   name + ": tmap Vt lo");
+        p.out_lo = out.C;
+        set_passes(p);
+      }
       finalize_or_throw(&p, name + ".pv");
       push(name + ".pv", 1, 2.0 * B * heads * (double)T * T * d, (double)s_bytes + 2.0 * B * T * C * 2,
            [p](cudaStream_t s) { return igemm_launch(p, s); });
@@ -448,7 +507,10 @@ void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk
     a.srcs = {l}; a.ks = 1; a.w = &wqk; a.out = qk;
     conv(name + ".to_qk", a);
   }
-  const size_t vt_bytes = (size_t)B * C * Tp * 2;
+  const int PL = split_ ? 2 : 1;
+  const long long TpP = (long long)Tp * PL;
+  GP_REQUIRE(wv.planes == PL && wqk.planes == PL, name + ": packed weights do not match the engine's precision mode");
+  const size_t vt_bytes = (size_t)B * C * TpP * 2;
   const size_t vt_off = arena_.alloc(vt_bytes);
   if (!measuring_) {   // V^T[b] = Wv . l[b]^T : A = weights (rows = channels), B = tokens
     IgemmParams p;
@@ -460,22 +522,35 @@ void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk
     p.nseg[0] = 1;
     p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)(wv.ktot / 64)};
     p.out = raw_ptr(vt_off); p.outW = C; p.outH = 1;
-    p.out_pix_stride = Tp; p.out_row_stride = 0;
-    p.out_z1 = (long long)C * Tp;
+    p.out_pix_stride = TpP; p.out_row_stride = 0;
+    p.out_z1 = (long long)C * TpP;
     p.out_sy = p.out_sx = 1;
     p.Cout = T;
     p.BN = choose_bn(T, 0);
-    check_cuda(make_tmap_a(&p.tmA[0], wv.w, wv.ktot, C, 1, 1, wv.ktot, (long long)C * wv.ktot, (long long)C * wv.ktot,
+    const long long wrow = (long long)wv.ktot * PL;
+    check_cuda(make_tmap_a(&p.tmA[0], wv.w, wv.ktot, C, 1, 1, wrow, (long long)C * wrow, (long long)C * wrow,
                            128, 1, bf16_), name + ": tmap Wv");
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
-    check_cuda(make_tmap_b(&p.tmB, ptr(l), C, T, B, C, (long long)T * C, p.BN, bf16_), name + ": tmap l");
+    check_cuda(make_tmap_b(&p.tmB, ptr(l), C, T, B, l.ps(), (long long)T * l.ps(), p.BN, bf16_), name + ": tmap l");
+    if (split_) {
+      check_cuda(make_tmap_a(&p.tmA[4], wv.w + wv.ktot, wv.ktot, C, 1, 1, wrow, (long long)C * wrow, (long long)C * wrow,
+                             128, 1, bf16_), name + ": tmap Wv lo");
+      for (int i = 5; i < 8; ++i) p.tmA[i] = p.tmA[4];
+      check_cuda(make_tmap_b(&p.tmB2, reinterpret_cast<const uint16_t*>(ptr(l)) + C, C, T, B, l.ps(), (long long)T * l.ps(), p.BN, bf16_),
+                 name + ": tmap l lo");
+      p.npass = 3;
+      p.pass_amap[0] = 0; p.pass_amap[1] = 4; p.pass_amap[2] = 0;
+      p.pass_bmap[0] = 0; p.pass_bmap[1] = 0; p.pass_bmap[2] = 1;
+      p.out_lo = Tp;
+    }
     finalize_or_throw(&p, name + ".to_vT");
     push(name + ".to_vT", 1, 2.0 * B * (double)T * C * C, (double)vt_bytes + (double)l.bytes(),
          [p](cudaStream_t s) { return igemm_launch(p, s); });
     ops.back().kind = 1;
   }
   const uint16_t* qp = measuring_ ? nullptr : reinterpret_cast<const uint16_t*>(ptr(qk));
-  attention_qkv(name, qp, qp ? qp + C : nullptr, 2 * C, measuring_ ? nullptr : raw_ptr(vt_off), B, T, heads, d, pv_bias, out);
+  attention_qkv(name, qp, qp ? qp + C : nullptr, qk.ps(), measuring_ ? nullptr : raw_ptr(vt_off), B, T, heads, d, pv_bias, out,
+                split_ ? 2LL * C : 0);
   arena_.release(vt_off);
   release(qk);
 }
@@ -518,18 +593,19 @@ void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const Nor
     void* y = ptr(out);
     const float* gamma = nw.gamma;
     const float* beta = nw.beta;
+    const bool sp = split_;
     push(name, launches, 0, bytes, [=](cudaStream_t s) {
       cudaError_t e;
       for (size_t i = 0; i < xs.size(); ++i) {
         if (!need[i]) continue;
-        e = gn_stats(xs[i], N, HW, cs[i], const_cast<float*>(gs[i].partial), chunks, cs[i], 0, bf, s);
+        e = gn_stats(xs[i], N, HW, cs[i], const_cast<float*>(gs[i].partial), chunks, cs[i], 0, bf, s, sp);
         if (e != cudaSuccess) return e;
       }
       e = gn_finalize(gs.data(), (int)gs.size(), gamma, beta, N, ctot, groups, HW, eps, ss, s);
       if (e != cudaSuccess) return e;
       int coff = 0;
       for (size_t i = 0; i < xs.size(); ++i) {
-        e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s);
+        e = gn_apply(xs[i], N, HW, cs[i], ss, ctot, coff, y, ctot, silu, bf, s, sp);
         if (e != cudaSuccess) return e;
         coff += cs[i];
       }
@@ -550,7 +626,8 @@ void Builder::ln(const std::string& name, const T4& x, const NormW& nw, float ep
   const bool bf = bf16_;
   const float* g = nw.gamma;
   const float* b = nw.beta;
-  push(name, 1, 0, 2.0 * x.bytes(), [=](cudaStream_t s) { return layernorm(xi, yo, tokens, C, g, b, eps, bf, s); });
+  const bool sp = split_;
+  push(name, 1, 0, 2.0 * x.bytes(), [=](cudaStream_t s) { return layernorm(xi, yo, tokens, C, g, b, eps, bf, s, sp); });
 }
 
 void Builder::xattn(const std::string& name, const T4& x, const XattnW& w, float eps, const T4& out) {
@@ -559,10 +636,10 @@ void Builder::xattn(const std::string& name, const T4& x, const XattnW& w, float
   const void* xi = ptr(x);
   void* yo = ptr(out);
   const long long tokens = x.pixels();
-  const bool bf = bf16_;
+  const bool bf = bf16_, sp = split_;
   const XattnW ww = w;
   push(name, 1, 4.0 * tokens * (double)w.C * w.heads, 2.0 * x.bytes(), [=](cudaStream_t s) {
-    return xattn2(xi, yo, tokens, ww.C, ww.heads, ww.U, ww.u0, ww.M, ww.c0, eps, bf, s);
+    return xattn2(xi, yo, tokens, ww.C, ww.heads, ww.U, ww.u0, ww.M, ww.c0, eps, bf, s, sp);
   });
 }
 
@@ -582,7 +659,8 @@ void Builder::relu_op(const std::string& name, const T4& in, const T4& out) {
   void* yo = ptr(out);
   const long long n = in.pixels() * in.C;
   const bool bf = bf16_;
-  push(name, 1, 0, 2.0 * in.bytes(), [=](cudaStream_t s) { return relu16(xi, yo, n, bf, s); });
+  const int sc = split_ ? in.C : 0;
+  push(name, 1, 0, 2.0 * in.bytes(), [=](cudaStream_t s) { return relu16(xi, yo, n, bf, s, sc); });
 }
 
 void Builder::bilinear(const std::string& name, const T4& in, const T4& out) {
@@ -592,7 +670,8 @@ void Builder::bilinear(const std::string& name, const T4& in, const T4& out) {
   void* yo = ptr(out);
   const T4 t = in;
   const bool bf = bf16_;
-  push(name, 1, 0, (double)in.bytes() + out.bytes(), [=](cudaStream_t s) { return bilinear_up2x(xi, yo, t.N, t.H, t.W, t.C, bf, s); });
+  const bool sp = split_;
+  push(name, 1, 0, (double)in.bytes() + out.bytes(), [=](cudaStream_t s) { return bilinear_up2x(xi, yo, t.N, t.H, t.W, t.C, bf, s, sp); });
 }
 
 void Builder::direct(const std::string& name, const T4& in, int cin, const DirectW& w, const T4& out, int flags,
@@ -602,14 +681,15 @@ void Builder::direct(const std::string& name, const T4& in, int cin, const Direc
   DirectConvParams p;
   std::memset(&p, 0, sizeof(p));
   p.in = ptr(in);
-  p.N = in.N; p.H = in.H; p.W = in.W; p.Cin = cin; p.in_cstride = in.C;
+  p.N = in.N; p.H = in.H; p.W = in.W; p.Cin = cin; p.in_cstride = (int)in.ps();
+  p.in_lo = split_ ? in.C : 0;
   p.w = w.w; p.bias = w.bias;
   p.Ho = up ? 2 * in.H : in.H; p.Wo = up ? 2 * in.W : in.W;
   p.Cout = w.Cout;
   p.ks = w.ks; p.stride = 1; p.pad = w.ks / 2;
   p.flags = flags | (up ? DC_UP2X : 0) | (out_f32 ? DC_OUT_F32_NCHW : 0);
   if (out_f32) { p.out = out_f32; p.out_cstride = w.Cout; }
-  else { p.out = ptr(out); p.out_cstride = out.C; }
+  else { p.out = ptr(out); p.out_cstride = (int)out.ps(); p.out_lo = split_ ? out.C : 0; }
   const bool bf = bf16_;
   const double flops = 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * cin * w.ks * w.ks;
   push(name, 1, flops, (double)in.bytes() + (double)p.N * p.Ho * p.Wo * p.Cout * (out_f32 ? 4 : 2),

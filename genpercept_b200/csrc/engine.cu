@@ -91,6 +91,7 @@ struct Plan {
 struct gp_engine {
   gp_config cfg;
   bool bf16 = false;
+  bool split = false;        // cfg.precision == 1: (hi, lo) fp16 pairs everywhere (engine.h T4::planes, PackedW::planes)
   std::string err;
   bool poisoned = false, finalized = false;
   std::unordered_map<std::string, HostT> host;
@@ -133,19 +134,23 @@ struct gp_engine {
     int ktot = 0;
     for (auto& s : classes[0]) ktot += ceil_div_i(s.C, 64) * 64;
     w.ktot = ktot;
-    std::vector<uint16_t> buf((size_t)w.nz * rows * ktot, 0);
-    const bool bf = bf16;
+    w.planes = split ? 2 : 1;
+    const size_t rowlen = (size_t)ktot * w.planes;       // [ktot hi | ktot lo]
+    std::vector<uint16_t> buf((size_t)w.nz * rows * rowlen, 0);
+    const bool bf = bf16, sp = split;
     for (int z = 0; z < w.nz; ++z) {
       const auto& segs = classes[z];
-      uint16_t* base = buf.data() + (size_t)z * rows * ktot;
+      uint16_t* base = buf.data() + (size_t)z * rows * rowlen;
       parallel_for(rows, [&, base](int co) {
-        uint16_t* row = base + (size_t)co * ktot;
+        uint16_t* row = base + (size_t)co * rowlen;
         int k0 = 0;
         for (auto& sg : segs) {
           for (int c = 0; c < sg.C; ++c) {
             float v = 0.f;
             for (auto& t : sg.terms) v += t.coef * t.p[co * t.sco + c * t.sc];
-            row[k0 + c] = host_f2h(v, bf);
+            const uint16_t hi = host_f2h(v, bf);
+            row[k0 + c] = hi;
+            if (sp) row[ktot + k0 + c] = host_f2h(v - host_h2f(hi, bf), bf);
           }
           k0 += ceil_div_i(sg.C, 64) * 64;
         }
@@ -519,9 +524,9 @@ struct gp_engine {
         void* sp = b.ptr(sc);
         const long long rows = (long long)x.N * x.H * x.W;
         const int kp = xg.Kp, nh = heads, nt = n_tokens;
-        const bool bf = bf16;
+        const bool bf = bf16, spl = split;
         b.custom(blk + ".attn2.softmax", 1, 2.0 * rows * kp * 2,
-                 [=](cudaStream_t s) { return softmax_groups(sp, rows, kp, nh, nt, bf, s); });
+                 [=](cudaStream_t s) { return softmax_groups(sp, rows, kp, nh, nt, bf, s, spl); });
       }
       { ConvArgs c; c.srcs = {sc}; c.ks = 1; c.w = xg.B; c.out = t2; c.res1 = &t1; b.conv(blk + ".attn2.out", c); }
       b.release(sc);
@@ -723,7 +728,7 @@ struct gp_engine {
           if (!b.measuring()) {
             const void* src = b.ptr(cur);
             void* dst = b.ptr(up);
-            const int n = cur.N, h = cur.H, w = cur.W, oh = nxt.H, ow = nxt.W, ch = cur.C;
+            const int n = cur.N, h = cur.H, w = cur.W, oh = nxt.H, ow = nxt.W, ch = (int)cur.ps();   // both planes move together
             b.custom(k + ".nearest", 1, (double)cur.bytes() + (double)up.bytes(),
                      [=](cudaStream_t s) { return nearest_resize(src, dst, n, h, w, oh, ow, ch, s); });
           }
@@ -992,6 +997,8 @@ gp_status gp_create(const gp_config* cfg, gp_engine** out) {
   e->cfg = *cfg;
   if (e->cfg.timestep <= 0) e->cfg.timestep = 1;
   e->bf16 = cfg->dtype == GP_BF16;
+  e->split = cfg->precision == 1;
+  if (cfg->precision != 0 && cfg->precision != 1) { delete e; return GP_ERR_INVALID; }
   *out = e;
   return GP_OK;
 }
@@ -1040,7 +1047,7 @@ gp_status gp_finalize(gp_engine* e) {
     GP_REQUIRE(e->n_tokens > 0, "gp_finalize: text embedding not set");
     GP_CUDA(cudaSetDevice(e->cfg.device));
     // A measuring pass over a nominal shape touches every weight the topology needs: packs + uploads.
-    Builder b(e->bf16, true, nullptr);
+    Builder b(e->bf16, true, nullptr, e->split);
     e->build(b, nullptr, 1, 64, 64);
     e->folded.clear();
     e->host.clear();
@@ -1056,14 +1063,14 @@ gp_status gp_plan(gp_engine* e, int B, int H, int W) {
     auto key = std::make_tuple(B, H, W);
     auto it = e->plans.find(key);
     if (it != e->plans.end()) { e->cur = it->second.get(); return; }
-    Builder m(e->bf16, true, nullptr);
+    Builder m(e->bf16, true, nullptr, e->split);
     e->build(m, nullptr, B, H, W);
     std::unique_ptr<Plan> p(new Plan());
     p->B = B; p->H = H; p->W = W;
     p->arena_bytes = m.arena_bytes();
     GP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->arena), p->arena_bytes));
     GP_CUDA(cudaMemset(p->arena, 0, p->arena_bytes));
-    Builder b(e->bf16, false, p->arena);
+    Builder b(e->bf16, false, p->arena, e->split);
     e->build(b, p.get(), B, H, W);
     if (b.arena_bytes() != p->arena_bytes) throw GpError(GP_ERR_STATE, "planner passes disagree on arena size");
     p->ops = std::move(b.ops);
@@ -1094,7 +1101,7 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
     else if (rgb_dtype == GP_F32) { kind = 2; esz = 4; }
     else throw GpError(GP_ERR_INVALID, "gp_infer: rgb dtype must be u8, f16 or f32");
     GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, npix * 3 * esz, rgb_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    GP_CUDA(preprocess_rgb(p->in_staging, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s));
+    GP_CUDA(preprocess_rgb(p->in_staging, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
     // 2 = auto: replay a graph where the launch stream is the bottleneck — small plans (measured: +15 % at 384x384,
     // +8 % at 768x768 with one image, nothing at batch 8)
     const bool use_graph = e->cfg.use_cuda_graph == 1 ||
@@ -1162,13 +1169,16 @@ gp_status gp_read_tensor(gp_engine* e, const char* name, float* host_out, size_t
     const T4& t = it->second.t;
     const int cr = it->second.creal;
     GP_REQUIRE(cap >= (size_t)t.N * cr * t.H * t.W, "gp_read_tensor: buffer too small");
-    std::vector<uint16_t> h((size_t)t.N * t.H * t.W * t.C);
+    const size_t ps = (size_t)t.ps();
+    std::vector<uint16_t> h((size_t)t.N * t.H * t.W * ps);
     GP_CUDA(cudaMemcpy(h.data(), p->arena + t.off, h.size() * 2, cudaMemcpyDeviceToHost));
     const size_t HW = (size_t)t.H * t.W;
     for (int n = 0; n < t.N; ++n)
       for (size_t px = 0; px < HW; ++px)
-        for (int c = 0; c < cr; ++c)
-          host_out[((size_t)n * cr + c) * HW + px] = host_h2f(h[((size_t)n * HW + px) * t.C + c], e->bf16);
+        for (int c = 0; c < cr; ++c) {
+          const uint16_t* q = &h[((size_t)n * HW + px) * ps + c];
+          host_out[((size_t)n * cr + c) * HW + px] = host_h2f(q[0], e->bf16) + (t.planes == 2 ? host_h2f(q[t.C], e->bf16) : 0.f);
+        }
   });
 }
 
@@ -1181,12 +1191,17 @@ gp_status gp_write_tensor(gp_engine* e, const char* name, const float* host_in, 
     const T4& t = it->second.t;
     const int cr = it->second.creal;
     GP_REQUIRE(elems == (size_t)t.N * cr * t.H * t.W, "gp_write_tensor: size mismatch");
-    std::vector<uint16_t> h((size_t)t.N * t.H * t.W * t.C, 0);
+    const size_t ps = (size_t)t.ps();
+    std::vector<uint16_t> h((size_t)t.N * t.H * t.W * ps, 0);
     const size_t HW = (size_t)t.H * t.W;
     for (int n = 0; n < t.N; ++n)
       for (size_t px = 0; px < HW; ++px)
-        for (int c = 0; c < cr; ++c)
-          h[((size_t)n * HW + px) * t.C + c] = host_f2h(host_in[((size_t)n * cr + c) * HW + px], e->bf16);
+        for (int c = 0; c < cr; ++c) {
+          const float v = host_in[((size_t)n * cr + c) * HW + px];
+          uint16_t* q = &h[((size_t)n * HW + px) * ps + c];
+          q[0] = host_f2h(v, e->bf16);
+          if (t.planes == 2) q[t.C] = host_f2h(v - host_h2f(q[0], e->bf16), e->bf16);
+        }
     GP_CUDA(cudaDeviceSynchronize());
     GP_CUDA(cudaMemcpy(p->arena + t.off, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   });

@@ -42,6 +42,7 @@ struct HostT {
 struct PackedW {
   uint16_t* w = nullptr;
   int rows = 0, ktot = 0, nz = 1;
+  int planes = 1;            // 2 in the high-precision mode: every row is [ktot hi | ktot lo] (value = hi + lo)
   float* bias = nullptr;
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
@@ -54,11 +55,14 @@ struct SegSpec { std::vector<Term> terms; int C; };
 
 // dense 16-bit NHWC activation; `off` is a byte offset into the arena (or an absolute address
 // when the builder's base is null).
+// High-precision mode: planes == 2, a pixel holds [hi C | lo C] (two fp16 planes, value = hi + lo).
 struct T4 {
   long long off = -1;
   int N = 0, H = 0, W = 0, C = 0;
-  size_t bytes() const { return (size_t)N * H * W * C * 2; }
+  int planes = 1;
+  size_t bytes() const { return (size_t)N * H * W * C * 2 * planes; }
   long long pixels() const { return (long long)N * H * W; }
+  long long ps() const { return (long long)C * planes; }      // elements between consecutive pixels
 };
 
 class Arena {
@@ -101,7 +105,8 @@ struct ConvArgs {
 
 class Builder {
  public:
-  Builder(bool bf16, bool measuring, uint8_t* base);
+  Builder(bool bf16, bool measuring, uint8_t* base, bool split = false);
+  bool split() const { return split_; }
   T4 alloc(int N, int H, int W, int C);
   T4 external(const void* p, int N, int H, int W, int C) const;
   void release(const T4& t);
@@ -114,7 +119,7 @@ class Builder {
   void attention(const std::string& name, const T4& l, const PackedW& wqk, const PackedW& wv, const float* pv_bias,
                  int heads, const T4& out);
   void attention_qkv(const std::string& name, const void* q, const void* k, long long qk_cstride, const void* vT, int B,
-                     int T, int heads, int d, const float* pv_bias, const T4& out);
+                     int T, int heads, int d, const float* pv_bias, const T4& out, long long qk_lo = 0);
   void gn(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps, bool silu,
           const T4& out);
   void ln(const std::string& name, const T4& x, const NormW& nw, float eps, const T4& out);
@@ -142,7 +147,7 @@ class Builder {
  private:
   void push(const std::string& name, int launches, double flops, double bytes,
             std::function<cudaError_t(cudaStream_t)> fn);
-  bool bf16_, measuring_;
+  bool bf16_, measuring_, split_ = false;
   uint8_t* base_;
   Arena arena_;
 };

@@ -80,6 +80,26 @@ __device__ __forceinline__ void add8(float* v, const uint4& u) {
   }
 }
 
+// 8 consecutive channels -> one 16-byte store; in the high-precision layout (lo != 0) the rounding residual
+// v - float(hi) goes to the lo plane `lo` elements further.
+template <bool BF16>
+__device__ __forceinline__ void store8_hl(uint16_t* op, long long lo, const float* v) {
+  uint4 u;
+  u.x = pack16<BF16>(v[0], v[1]);
+  u.y = pack16<BF16>(v[2], v[3]);
+  u.z = pack16<BF16>(v[4], v[5]);
+  u.w = pack16<BF16>(v[6], v[7]);
+  *reinterpret_cast<uint4*>(op) = u;
+  if (lo) {
+    const uint32_t hw[4] = {u.x, u.y, u.z, u.w};
+    uint32_t lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      lw[e] = pack16<BF16>(v[2 * e] - cvt16<BF16>((uint16_t)(hw[e] & 0xFFFF)), v[2 * e + 1] - cvt16<BF16>((uint16_t)(hw[e] >> 16)));
+    *reinterpret_cast<uint4*>(op + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // gelu(g) = g * Phi(g), exact-erf form (what diffusers' GEGLU uses), with erf from Abramowitz-Stegun 7.1.26
 // (|error| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner instead of erff()'s two-branch
 // polynomial — the GEGLU projection is bound by its epilogue (tensor pipe 33 %, ncu r1_final).
@@ -117,6 +137,8 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   uint8_t* stg = stg_base + wq * 4096;
   const uint32_t stg_addr = smem_u32(stg);
   const uint32_t my_row = stg_addr + lane * 128;
+  const bool split = p.out_lo != 0;          // high-precision mode: a second staged tile (+16 KiB) takes the lo plane
+  const uint32_t my_row_lo = my_row + 4 * 4096;
   const int sw = lane & 7;
   int acc = 0;
   uint32_t acc_phase = 0, res_phase = 0;
@@ -278,6 +300,18 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
 #pragma unroll
             for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], r2[q]);
           }
+          if (split) {       // lo planes of the residuals
+            if (has1) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off + p.out_lo);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], rp[q]);
+            }
+            if (has2) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off + p.out_lo);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) add8<BF16>(&v[q * 8], rp[q]);
+            }
+          }
           if (relu) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -289,16 +323,26 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t a = my_row + (((sub * 4 + i) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16<BF16>(v[8 * i], v[8 * i + 1])),
-                         "r"(pack16<BF16>(v[8 * i + 2], v[8 * i + 3])), "r"(pack16<BF16>(v[8 * i + 4], v[8 * i + 5])),
-                         "r"(pack16<BF16>(v[8 * i + 6], v[8 * i + 7]))
-                         : "memory");
+            const uint32_t h0 = pack16<BF16>(v[8 * i], v[8 * i + 1]), h1 = pack16<BF16>(v[8 * i + 2], v[8 * i + 3]);
+            const uint32_t h2 = pack16<BF16>(v[8 * i + 4], v[8 * i + 5]), h3 = pack16<BF16>(v[8 * i + 6], v[8 * i + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+            if (split) {     // lo = v - float(hi), rounded to 16 bit
+              const uint32_t hw[4] = {h0, h1, h2, h3};
+              uint32_t lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                lw[e] = pack16<BF16>(v[8 * i + 2 * e] - cvt16<BF16>((uint16_t)(hw[e] & 0xFFFF)),
+                                     v[8 * i + 2 * e + 1] - cvt16<BF16>((uint16_t)(hw[e] >> 16)));
+              const uint32_t al = my_row_lo + (((sub * 4 + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(al), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+            }
           }
         }
         fence_proxy_async_shared();
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&p.tmOut[cls], stg_addr, n0, sx, sy, t.z1);
+          if (split) tma_store_4d(&p.tmOutLo[cls], stg_addr + 4 * 4096, n0, sx, sy, t.z1);
           tma_store_commit();
         }
         if (do_stats) {
@@ -338,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int stage_bytes = a_bytes + p.BN * 128;
   const int stages = p.stages;
   uint8_t* stg_base = smem + stages * stage_bytes;                     // 4 x 4 KiB staging tiles (tma_store only)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? (p.out_lo ? 8 : 4) * 4096 : 0));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -350,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+    for (int i = 0; i < (p.npass > 1 ? 8 : 4); ++i) tma_prefetch_desc(&p.tmA[i]);
     tma_prefetch_desc(&p.tmB);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 2);    // producer A + producer B
@@ -383,18 +427,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int a_k0 = t.z0 * p.a_k_z0;
       const int x0 = t.tx * p.TW, y0 = t.ty * p.TH;
       const int ns = p.nseg[cls];
-      for (int s = 0; s < ns; ++s) {
-        const IgemmSeg sg = p.seg[cls][s];
-        const CUtensorMap* tm = &p.tmA[sg.map];
-        const int xs = x0 + sg.dx, ys = y0 + sg.dy;
-        for (int c = 0; c < sg.nchunks; ++c) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          if (leader) {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
-            tma_load_4d(smem + stage * stage_bytes, tm, &full_bar[stage], a_k0 + c * kBK, xs, ys, a_n);
+      for (int pass = 0; pass < p.npass; ++pass) {
+        const int moff = p.pass_amap[pass];
+        for (int s = 0; s < ns; ++s) {
+          const IgemmSeg sg = p.seg[cls][s];
+          const CUtensorMap* tm = &p.tmA[sg.map + moff];
+          const int xs = x0 + sg.dx, ys = y0 + sg.dy;
+          for (int c = 0; c < sg.nchunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            if (leader) {
+              mbar_expect_tx(&full_bar[stage], (uint32_t)a_bytes);
+              tma_load_4d(smem + stage * stage_bytes, tm, &full_bar[stage], a_k0 + c * kBK, xs, ys, a_n);
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -411,14 +458,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int b_row = t.z0 * p.b_row_z0 + t.n_tile * p.BN;
       const int b_k0 = t.z0 * p.b_k_z0;
       const int nkb = p.nkb[cls];
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, 5);
-        if (leader) {
-          mbar_expect_tx(&full_bar[stage], b_bytes);
-          tma_load_3d(smem + stage * stage_bytes + a_bytes, &p.tmB, &full_bar[stage], b_k0 + kb * kBK, b_row, b_z);
+      for (int pass = 0; pass < p.npass; ++pass) {
+        const CUtensorMap* tmb = p.pass_bmap[pass] ? &p.tmB2 : &p.tmB;
+        const int bk = b_k0 + p.pass_bk[pass];
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 5);
+          if (leader) {
+            mbar_expect_tx(&full_bar[stage], b_bytes);
+            tma_load_3d(smem + stage * stage_bytes + a_bytes, tmb, &full_bar[stage], bk + kb * kBK, b_row, b_z);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 5 || (warp == 6 && p.MT == 2)) {
@@ -436,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int cls = p.cls_from_z0 ? t.z0 : 0;
-      const int nkb = p.nkb[cls];
+      const int nkb = p.nkb[cls] * p.npass;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -590,6 +641,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
             for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
           }
+          if (p.out_lo) {      // high-precision layout: lo planes of the residuals
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri) {
+              const void* rb = ri == 0 ? p.res1 : p.res2;
+              if (rb == nullptr || !live) continue;
+              const uint16_t* rp = reinterpret_cast<const uint16_t*>(rb) + off + p.out_lo;
+              if (vec) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], reinterpret_cast<const uint4*>(rp)[q]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
+              }
+            }
+          }
           if (relu) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -600,33 +666,23 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
             for (int q = 0; q < 16; ++q) g[q] = v[q] * gelu_erf(v[16 + q]);
 #pragma unroll
-            for (int q = 0; q < 16; q += 8) {
-              uint4 u;
-              u.x = pack16<BF16>(g[q], g[q + 1]);
-              u.y = pack16<BF16>(g[q + 2], g[q + 3]);
-              u.z = pack16<BF16>(g[q + 4], g[q + 5]);
-              u.w = pack16<BF16>(g[q + 6], g[q + 7]);
-              *reinterpret_cast<uint4*>(og + q) = u;
-            }
+            for (int q = 0; q < 16; q += 8) store8_hl<BF16>(og + q, p.out_lo, &g[q]);
             continue;
           }
           uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
           if (vec) {
 #pragma unroll
             for (int q = 0; q < 32; q += 8) {
-              if (q < ncols) {
-                uint4 u;
-                u.x = pack16<BF16>(v[q], v[q + 1]);
-                u.y = pack16<BF16>(v[q + 2], v[q + 3]);
-                u.z = pack16<BF16>(v[q + 4], v[q + 5]);
-                u.w = pack16<BF16>(v[q + 6], v[q + 7]);
-                *reinterpret_cast<uint4*>(op + q) = u;
-              }
+              if (q < ncols) store8_hl<BF16>(op + q, p.out_lo, &v[q]);
             }
           } else if (live) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              if (q < nvalid) op[q] = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
+              if (q < nvalid) {
+                const uint16_t h = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
+                op[q] = h;
+                if (p.out_lo) op[q + p.out_lo] = (uint16_t)(pack16<BF16>(v[q] - cvt16<BF16>(h), 0.f) & 0xFFFF);
+              }
             }
           }
         }
@@ -851,6 +907,11 @@ size_t igemm_smem_bytes(const IgemmParams& p) {
 
 const char* igemm_finalize(IgemmParams* p) {
   if (p->MT == 0) p->MT = 1;
+  if (p->npass == 0) p->npass = 1;
+  if (p->npass != 1 && p->npass != 3) return "npass must be 1 or 3";
+  if (p->npass == 1) { p->pass_amap[0] = 0; p->pass_bk[0] = 0; p->pass_bmap[0] = 0; }
+  if (p->out_lo && (p->stats || p->res_tma || p->patch || (p->flags & IG_OUT_F32_NCHW)))
+    return "the high-precision output layout excludes epilogue statistics, TMA residuals, the patch loop and fp32 maps";
   if (p->MT != 1 && p->MT != 2) return "MT must be 1 or 2";
   if (p->MT == 2 && p->BN > 128) return "MT=2 needs BN <= 128 (TMEM: 2 buffers x 2 tiles x BN columns)";
   if (p->TW * p->TH != kBM * p->MT) return "TW*TH must be 128*MT";
@@ -879,7 +940,7 @@ const char* igemm_finalize(IgemmParams* p) {
     return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
   if (p->tma_store && (p->flags & IG_GEGLU) && ((p->Cout % 128) || (p->BN % 128))) return "staged GEGLU needs Cout, BN % 128 == 0";
   if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
-  int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0)) / stage_bytes;
+  int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? (p->out_lo ? 8 : 4) * 4096 : 0)) / stage_bytes;
   if (p->patch) {
     if (!p->tma_store || p->MT != 2 || p->TW != 128 || p->TH != 2 || p->Z0 != 1 || p->nseg[0] != 9 || p->n_tiles_n < 1)
       return "patch mode needs the staged epilogue, TW = 128, MT = 2 and a single-source 3x3 tap table";

@@ -38,8 +38,19 @@ enum IgemmFlags : int {
 };
 
 struct IgemmParams {
-  CUtensorMap tmA[4];
+  CUtensorMap tmA[8];            // [0..3]: the (hi) planes of up to 4 sources; [4..7]: their lo planes (high-precision mode)
   CUtensorMap tmB;
+  CUtensorMap tmB2;              // lo plane of an ACTIVATION B operand (attention GEMMs, high-precision mode)
+  // High-precision mode (gp_config::precision = 1): every operand is an fp16 (hi, lo) pair and the K loop runs
+  // three passes over the segment table, accumulating hi*hi + lo*hi + hi*lo in the same fp32 TMEM accumulator.
+  // Packed weights carry both planes along K: [.. ktot hi .. | .. ktot lo ..].
+  int npass;                     // 1, or 3
+  int pass_amap[3];              // added to IgemmSeg::map          {0, 4, 0}
+  int pass_bk[3];                // added to the B K coordinate      {0, 0, ktot}
+  int pass_bmap[3];              // 0: tmB, 1: tmB2                  {0, 0, 0 or 1}
+  long long out_lo;              // element offset of the output's lo plane inside a pixel (0: plain 16-bit output);
+                                 // residuals share the output's layout
+  CUtensorMap tmOutLo[kMaxClasses];
   IgemmSeg seg[kMaxClasses][kMaxSegs];
   int nseg[kMaxClasses];
   int nkb[kMaxClasses];          // total K blocks per class

@@ -42,6 +42,44 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// High-precision (split) layout: a tensor with C logical channels is stored with 2C physical channels per pixel,
+// [hi C | lo C], value = hi + lo (two fp16: ~22 mantissa bits).  `lo` = element offset of the lo plane (0 = plain).
+template <bool BF16>
+__device__ __forceinline__ void load8(const uint16_t* p, int lo, float (&f)[8]) {
+  unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  if (lo) {
+    float g[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(p + lo)), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] += g[e];
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ void store8(uint16_t* p, int lo, const float (&f)[8]) {
+  const uint4 h = pack8<BF16>(f);
+  *reinterpret_cast<uint4*>(p) = h;
+  if (lo) {
+    float hf[8], r[8];
+    unpack8<BF16>(h, hf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = f[e] - hf[e];
+    *reinterpret_cast<uint4*>(p + lo) = pack8<BF16>(r);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float load1(const uint16_t* p, int lo) {
+  float v = f16_to_f32<BF16>(*p);
+  if (lo) v += f16_to_f32<BF16>(p[lo]);
+  return v;
+}
+template <bool BF16>
+__device__ __forceinline__ void store1(uint16_t* p, int lo, float v) {
+  const uint16_t h = f32_to_f16<BF16>(v);
+  *p = h;
+  if (lo) p[lo] = f32_to_f16<BF16>(v - f16_to_f32<BF16>(h));
+}
+// fp32-class SiLU for the high-precision mode (tanh.approx carries only ~11 bits)
+__device__ __forceinline__ float silu_precise(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -79,17 +117,17 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
       if (up) ix >>= 1;
       const uint16_t* xp = in + (((long long)n * p.H + iy) * p.W + ix) * p.in_cstride;
       const float* wp = p.w + ((long long)(ky * p.ks + kx) * p.Cin) * p.Cout + co;
-      for (int ci = 0; ci < p.Cin; ++ci) acc += f16_to_f32<BF16>(xp[ci]) * wp[(long long)ci * p.Cout];
+      for (int ci = 0; ci < p.Cin; ++ci) acc += load1<BF16>(xp + ci, p.in_lo) * wp[(long long)ci * p.Cout];
     }
   }
   const long long opix = ((long long)n * p.Ho + oy) * p.Wo + ox;
-  if (p.res) acc += f16_to_f32<BF16>(reinterpret_cast<const uint16_t*>(p.res)[opix * p.out_cstride + co]);
+  if (p.res) acc += load1<BF16>(reinterpret_cast<const uint16_t*>(p.res) + opix * p.out_cstride + co, p.out_lo);
   if (p.flags & DC_RELU) acc = fmaxf(acc, 0.f);
   if (p.flags & DC_AFFINE_CLAMP01) acc = fminf(fmaxf((acc + 1.f) * 0.5f, 0.f), 1.f);
   if (p.flags & DC_OUT_F32_NCHW) {
     reinterpret_cast<float*>(p.out)[(((long long)n * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = acc;
   } else {
-    reinterpret_cast<uint16_t*>(p.out)[opix * p.out_cstride + co] = f32_to_f16<BF16>(acc);
+    store1<BF16>(reinterpret_cast<uint16_t*>(p.out) + opix * p.out_cstride + co, p.out_lo, acc);
   }
 }
 
@@ -99,7 +137,7 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
 //   gn_finalize: one warp per (n, group) sums the partials in a fixed order -> scale/shift per channel
 template <bool BF16>
 __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, int C, float* __restrict__ partial,
-                                int Ctot, int coff, int pix_per_block) {
+                                int Ctot, int coff, int pix_per_block, int xs, int lo) {
   extern __shared__ float sh[];   // [PIX][C][2]
   const int n = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -110,13 +148,13 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-  const uint16_t* base = x + ((long long)n * HW) * C + threadIdx.x * 8;
+  const uint16_t* base = x + ((long long)n * HW) * xs + threadIdx.x * 8;
   const int step = blockDim.y;
   long long p = p0 + threadIdx.y;
-  for (; p + 3 * step < p1; p += 4 * step) {      // four independent 16-byte loads in flight
+  for (; p + 3 * step < p1 && !lo; p += 4 * step) {      // four independent 16-byte loads in flight
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + (long long)k * step) * C));
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + (long long)k * step) * xs));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
@@ -126,9 +164,8 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
     }
   }
   for (; p < p1; p += step) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * C));
     float f[8];
-    unpack8<BF16>(u, f);
+    load8<BF16>(base + p * xs, lo, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
   }
@@ -190,7 +227,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc s0, GnSrc s1, in
 
 template <bool BF16, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, int C, const float* __restrict__ ss,
-                                int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, int pix_per_block) {
+                                int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, int pix_per_block, int xs,
+                                int lo_x, int lo_y) {
   // blockDim = (C/8 channel vectors, PIX pixel lanes); grid = (pixel chunks, N).  The thread's 8
   // (scale, shift) pairs live in registers for its whole pixel strip.
   const int n = blockIdx.y;
@@ -206,14 +244,14 @@ __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, in
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > HW) p1 = HW;
-  const uint16_t* xb = x + ((long long)n * HW) * C + threadIdx.x * 8;
+  const uint16_t* xb = x + ((long long)n * HW) * xs + threadIdx.x * 8;
   uint16_t* yb = y + ((long long)n * HW) * y_cstride + coff + threadIdx.x * 8;
   const int step = blockDim.y;
   long long p = p0 + threadIdx.y;
-  for (; p + 3 * step < p1; p += 4 * step) {
+  for (; p + 3 * step < p1 && !lo_y; p += 4 * step) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (p + (long long)k * step) * C));
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (p + (long long)k * step) * xs));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
@@ -228,13 +266,13 @@ __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, in
   }
   for (; p < p1; p += step) {
     float f[8];
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(xb + p * C)), f);
+    load8<BF16>(xb + p * xs, lo_x, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = f[e] * sc[e] + sh[e];
-      f[e] = SILU ? silu_f(v) : v;
+      f[e] = SILU ? (lo_y ? silu_precise(v) : silu_f(v)) : v;
     }
-    *reinterpret_cast<uint4*>(yb + p * y_cstride) = pack8<BF16>(f);
+    store8<BF16>(yb + p * y_cstride, lo_y, f);
   }
 }
 
@@ -245,18 +283,19 @@ constexpr int kLnMaxVec = 5;   // C <= 1280
 template <bool BF16, int KV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens,
                                                         int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps) {
+                                                        float eps, int lo) {
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= tokens) return;
   const int nvec = C / 8;
+  const int xs = lo ? 2 * C : C;
   float f[KV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < KV; ++i) {
     const int v = lane + 32 * i;
     if (v < nvec) {
-      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + tok * C + v * 8)), f[i]);
+      load8<BF16>(x + tok * xs + v * 8, lo, f[i]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += f[i][e];
     }
@@ -282,7 +321,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
-      *reinterpret_cast<uint4*>(y + tok * C + v * 8) = pack8<BF16>(o);
+      store8<BF16>(y + tok * xs + v * 8, lo, o);
     }
   }
 }
@@ -290,27 +329,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
 // ------------------------------------------------------------------------------ row softmax
 constexpr int kSmMaxVec = 8;   // T <= 256 threads * 8 vec * 8 = 16384
 template <bool BF16>
-__global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long rows, int T, int Tp) {
+__global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long rows, int T, int Tp, int lo) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
-  uint16_t* row = s + r * Tp;
+  uint16_t* row = s + r * (lo ? 2 * Tp : Tp);
   float m = -INFINITY;
-  for (int i = lane; i < T; i += 32) m = fmaxf(m, f16_to_f32<BF16>(row[i]));
+  for (int i = lane; i < T; i += 32) m = fmaxf(m, load1<BF16>(row + i, lo));
   m = warp_max(m);
   float sum = 0.f;
-  for (int i = lane; i < T; i += 32) sum += __expf(f16_to_f32<BF16>(row[i]) - m);
+  for (int i = lane; i < T; i += 32) sum += __expf(load1<BF16>(row + i, lo) - m);
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int i = lane; i < T; i += 32) row[i] = f32_to_f16<BF16>(__expf(f16_to_f32<BF16>(row[i]) - m) * inv);
+  for (int i = lane; i < T; i += 32) store1<BF16>(row + i, lo, __expf(load1<BF16>(row + i, lo) - m) * inv);
 }
 
 // MV = 8-column vectors per thread: 8 (any T up to 16384, 256 threads) or 3 with 512 threads for T <= 12288 — the
 // VAE mid-block rows (T = 9216) then hold 24 values per thread instead of 64 (r1_final: 2.5 TB/s at low occupancy).
 template <bool BF16, int MV>
-__global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
+__global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp, int lo) {
   __shared__ float red[32];
-  uint16_t* row = s + (long long)blockIdx.x * Tp;
+  uint16_t* row = s + (long long)blockIdx.x * (lo ? 2 * Tp : Tp);
   const int nvec = T / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float f[MV][8];
@@ -319,7 +358,7 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
   for (int i = 0; i < MV; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
-      unpack8<BF16>(*reinterpret_cast<const uint4*>(row + v * 8), f[i]);
+      load8<BF16>(row + v * 8, lo, f[i]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) m = fmaxf(m, f[i][e]);
     }
@@ -350,7 +389,7 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
     if (v < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[i][e] *= inv;
-      *reinterpret_cast<uint4*>(row + v * 8) = pack8<BF16>(f[i]);
+      store8<BF16>(row + v * 8, lo, f[i]);
     }
   }
 }
@@ -361,11 +400,12 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp) {
 template <bool BF16, int KV, int TOK>
 __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens, int C,
                               int heads, const float* __restrict__ U, const float* __restrict__ u0,
-                              const float* __restrict__ M, const float* __restrict__ c0, float eps) {
+                              const float* __restrict__ M, const float* __restrict__ c0, float eps, int lo) {
   const int lane = threadIdx.x & 31;
   const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
   if (tok0 >= tokens) return;
   const int nvec = C / 8;
+  const int xs = lo ? 2 * C : C;
   float f[TOK][KV][8];
   float mean[TOK], rstd[TOK];
 #pragma unroll
@@ -376,7 +416,7 @@ __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restri
     for (int i = 0; i < KV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec && tv) {
-        unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + (tok0 + t) * C + v * 8)), f[t][i]);
+        load8<BF16>(x + (tok0 + t) * xs + v * 8, lo, f[t][i]);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[t][i][e] = 0.f;
@@ -451,7 +491,7 @@ __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restri
 #pragma unroll
       for (int i = 0; i < KV; ++i) {
         const int v = lane + 32 * i;
-        if (v < nvec) *reinterpret_cast<uint4*>(y + (tok0 + t) * C + v * 8) = pack8<BF16>(acc[t][i]);
+        if (v < nvec) store8<BF16>(y + (tok0 + t) * xs + v * 8, lo, acc[t][i]);
       }
     }
   }
@@ -475,22 +515,25 @@ __global__ void geglu_kernel(const uint16_t* __restrict__ in, uint16_t* __restri
 }
 
 template <bool BF16>
-__global__ void relu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec) {
+__global__ void relu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec, int nvec,
+                            int lo) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
+    const long long off = lo ? (i / nvec) * (2LL * lo) + (i % nvec) * 8 : i * 8;   // [pixel][hi C | lo C]
     float a[8];
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(in + i * 8)), a);
+    load8<BF16>(in + off, lo, a);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8<BF16>(a);
+    store8<BF16>(out + off, lo, a);
   }
 }
 
 template <bool BF16>
 __global__ void bilinear_up2x_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W,
-                                     int C, float sy, float sx, long long total_vec) {
+                                     int C, float sy, float sx, long long total_vec, int lo) {
   const int nvec = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
+  const int xs = lo ? 2 * C : C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % nvec);
@@ -503,21 +546,21 @@ __global__ void bilinear_up2x_kernel(const uint16_t* __restrict__ in, uint16_t* 
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
     const float h1 = fy - y0, w1 = fx - x0, h0 = 1.f - h1, w0 = 1.f - w1;
-    const uint16_t* b = in + ((long long)n * H * W) * C + v * 8;
+    const uint16_t* b = in + ((long long)n * H * W) * xs + v * 8;
     float a00[8], a01[8], a10[8], a11[8], o[8];
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x0) * C)), a00);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x1) * C)), a01);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x0) * C)), a10);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x1) * C)), a11);
+    load8<BF16>(b + ((long long)y0 * W + x0) * xs, lo, a00);
+    load8<BF16>(b + ((long long)y0 * W + x1) * xs, lo, a01);
+    load8<BF16>(b + ((long long)y1 * W + x0) * xs, lo, a10);
+    load8<BF16>(b + ((long long)y1 * W + x1) * xs, lo, a11);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = h0 * (w0 * a00[e] + w1 * a01[e]) + h1 * (w0 * a10[e] + w1 * a11[e]);
-    *reinterpret_cast<uint4*>(out + (((long long)n * Ho + oy) * Wo + ox) * C + v * 8) = pack8<BF16>(o);
+    store8<BF16>(out + (((long long)n * Ho + oy) * Wo + ox) * xs + v * 8, lo, o);
   }
 }
 
 template <bool BF16>
 __global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_t* __restrict__ out, int N,
-                                  long long HW) {
+                                  long long HW, int lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
   const int n = (int)(i / HW);
@@ -530,7 +573,7 @@ __global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_
     else if (kind == 1) f[c] = f16_to_f32<false>(reinterpret_cast<const uint16_t*>(in)[off]);
     else f[c] = reinterpret_cast<const float*>(in)[off];
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = pack8<BF16>(f);
+  store8<BF16>(out + i * (lo ? 16 : 8), lo, f);
 }
 
 __device__ __forceinline__ unsigned int f2ord(float f) {
@@ -600,7 +643,7 @@ int gn_chunks(int N, long long HW) {
 }
 
 cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, int chunks, int Ctot, int coff,
-                     bool bf16, cudaStream_t s) {
+                     bool bf16, cudaStream_t s, bool split) {
   const int nvec = C / 8;
   int pix = 256 / nvec;
   if (pix < 1) pix = 1;
@@ -610,7 +653,8 @@ cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, 
   dim3 grid((unsigned)chunks, N);
   const size_t smem = (size_t)pix * C * 2 * sizeof(float);
   GP_DISPATCH_BF16(bf16, (gn_stats_kernel<BF><<<grid, block, smem, s>>>(reinterpret_cast<const uint16_t*>(x), HW, C,
-                                                                         partial, Ctot, coff, pix_per_block)));
+                                                                         partial, Ctot, coff, pix_per_block,
+                                                                         split ? 2 * C : C, split ? C : 0)));
   return cudaGetLastError();
 }
 
@@ -624,7 +668,10 @@ cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const f
 }
 
 cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* ss, int Ctot, int coff, void* y,
-                     int y_cstride, bool silu, bool bf16, cudaStream_t s) {
+                     int y_cstride, bool silu, bool bf16, cudaStream_t s, bool split) {
+  // split: x carries [hi C | lo C] per pixel; y has y_cstride LOGICAL channels, i.e. [hi y_cstride | lo y_cstride]
+  const int xs = split ? 2 * C : C, lo_x = split ? C : 0, lo_y = split ? y_cstride : 0;
+  if (split) y_cstride *= 2;
   const int nvec = C / 8;
   int pix = 256 / nvec;
   if (pix < 1) pix = 1;
@@ -635,14 +682,15 @@ cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* ss,
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   if (silu)
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block)));
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
   else
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block)));
+    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
   return cudaGetLastError();
 }
 
 cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const float* gamma, const float* beta,
-                      float eps, bool bf16, cudaStream_t s) {
+                      float eps, bool bf16, cudaStream_t s, bool split) {
+  const int lo = split ? C : 0;
   if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
   const int tpb = 8;
   const long long blocks = (tokens + tpb - 1) / tpb;
@@ -650,19 +698,20 @@ cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const flo
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   const int kv = (C / 8 + 31) / 32;
   if (kv <= 2)
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 2><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps)));
+    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 2><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
   else if (kv <= 3)
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 3><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps)));
+    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 3><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
   else
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 5><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps)));
+    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 5><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
   return cudaGetLastError();
 }
 
-cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cudaStream_t s) {
+cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cudaStream_t s, bool split) {
+  const int lo = split ? Tp : 0;
   if (T % 8 || Tp % 8 || T < 64) {
     const int wpb = 8;
     GP_DISPATCH_BF16(bf16, (softmax_rows_small_kernel<BF><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(
-                               reinterpret_cast<uint16_t*>(sio), rows, T, Tp)));
+                               reinterpret_cast<uint16_t*>(sio), rows, T, Tp, lo)));
     return cudaGetLastError();
   }
   if (T / 8 > 256 * kSmMaxVec) return cudaErrorInvalidValue;
@@ -670,36 +719,37 @@ cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cu
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
   if (T / 8 > 256 && T / 8 <= 512 * 3) {
-    GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, 3><<<(unsigned)rows, 512, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
+    GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, 3><<<(unsigned)rows, 512, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
     return cudaGetLastError();
   }
-  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, kSmMaxVec><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp)));
+  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, kSmMaxVec><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
   return cudaGetLastError();
 }
 
 template <bool BF, int KV, int TOK>
 static cudaError_t xattn2_launch(const void* x, void* y, long long tokens, int C, int heads, const float* U, const float* u0,
-                                 const float* M, const float* c0, float eps, cudaStream_t s) {
+                                 const float* M, const float* c0, float eps, cudaStream_t s, int lo) {
   const int wpb = 8;
   const long long per_block = (long long)wpb * TOK;
   const long long blocks = (tokens + per_block - 1) / per_block;
   xattn2_kernel<BF, KV, TOK><<<(unsigned)blocks, wpb * 32, 0, s>>>(reinterpret_cast<const uint16_t*>(x),
                                                                     reinterpret_cast<uint16_t*>(y), tokens, C, heads, U, u0, M,
-                                                                    c0, eps);
+                                                                    c0, eps, lo);
   return cudaGetLastError();
 }
 
 cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, const float* U, const float* u0,
-                   const float* M, const float* c0, float eps, bool bf16, cudaStream_t s) {
+                   const float* M, const float* c0, float eps, bool bf16, cudaStream_t s, bool split) {
+  const int lo = split ? C : 0;
   if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
   const int kv = (C / 8 + 31) / 32;
   cudaError_t e = cudaSuccess;
   if (kv <= 2)
-    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 2, 2>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 2, 2>(x, y, tokens, C, heads, U, u0, M, c0, eps, s, lo)));
   else if (kv <= 3)
-    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 3, 1>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 3, 1>(x, y, tokens, C, heads, U, u0, M, c0, eps, s, lo)));
   else
-    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 5, 1>(x, y, tokens, C, heads, U, u0, M, c0, eps, s)));
+    GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 5, 1>(x, y, tokens, C, heads, U, u0, M, c0, eps, s, lo)));
   return e;
 }
 
@@ -710,28 +760,29 @@ cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16
   return cudaGetLastError();
 }
 
-cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s) {
-  const long long total_vec = n / 8;
+cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s, int split_c) {
+  const long long total_vec = n / 8;        // n = pixels * C logical elements
   GP_DISPATCH_BF16(bf16, (relu_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
-                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec)));
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec,
+                             split_c ? split_c / 8 : 1, split_c)));
   return cudaGetLastError();
 }
 
-cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16, cudaStream_t s) {
+cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16, cudaStream_t s, bool split) {
   const long long total_vec = (long long)N * 4 * H * W * (C / 8);
   const float sy = H > 1 ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float sx = W > 1 ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   GP_DISPATCH_BF16(bf16, (bilinear_up2x_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, C, sy,
-                             sx, total_vec)));
+                             sx, total_vec, split ? C : 0)));
   return cudaGetLastError();
 }
 
-cudaError_t preprocess_rgb(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s) {
+cudaError_t preprocess_rgb(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s, bool split) {
   const long long HW = (long long)H * W;
   const long long total = (long long)N * HW;
   GP_DISPATCH_BF16(bf16, (preprocess_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-                             in, in_kind, reinterpret_cast<uint16_t*>(out), N, HW)));
+                             in, in_kind, reinterpret_cast<uint16_t*>(out), N, HW, split ? 8 : 0)));
   return cudaGetLastError();
 }
 
@@ -764,28 +815,24 @@ __global__ void nearest_resize_kernel(const uint4* __restrict__ in, uint4* __res
 
 namespace {
 template <bool BF16>
-__global__ void softmax_groups_kernel(uint16_t* __restrict__ x, long long rows, int ld, int groups, int n) {
+__global__ void softmax_groups_kernel(uint16_t* __restrict__ x, long long rows, int ld, int groups, int n, int lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * groups) return;
-  uint16_t* p = x + (i / groups) * ld + (i % groups) * n;
-  auto ld16 = [](uint16_t v) { return BF16 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v)); };
+  uint16_t* p = x + (i / groups) * (lo ? 2 * ld : ld) + (i % groups) * n;
   float m = -INFINITY;
-  for (int j = 0; j < n; ++j) m = fmaxf(m, ld16(p[j]));
+  for (int j = 0; j < n; ++j) m = fmaxf(m, load1<BF16>(p + j, lo));
   float s = 0.f;
-  for (int j = 0; j < n; ++j) s += __expf(ld16(p[j]) - m);
+  for (int j = 0; j < n; ++j) s += __expf(load1<BF16>(p + j, lo) - m);
   const float inv = 1.f / s;
-  for (int j = 0; j < n; ++j) {
-    const float v = __expf(ld16(p[j]) - m) * inv;
-    p[j] = BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
-  }
+  for (int j = 0; j < n; ++j) store1<BF16>(p + j, lo, __expf(load1<BF16>(p + j, lo) - m) * inv);
 }
 }  // namespace
 
-cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s) {
+cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s, bool split) {
   if (groups < 1 || n < 1 || groups * n > ld) return cudaErrorInvalidValue;
   const long long total = rows * groups;
   GP_DISPATCH_BF16(bf16, (softmax_groups_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
-                             reinterpret_cast<uint16_t*>(x), rows, ld, groups, n)));
+                             reinterpret_cast<uint16_t*>(x), rows, ld, groups, n, split ? ld : 0)));
   return cudaGetLastError();
 }
 

@@ -2,6 +2,8 @@
 // GroupNorm(+SiLU), LayerNorm, row softmax, the 2-token cross-attention closed form, GEGLU,
 // ReLU, bilinear 2x, direct convolution for tiny channel counts (and as the on-device triage
 // reference for the tcgen05 kernel), pre/post-processing.  16-bit NHWC activations, fp32 math.
+// `split` = the high-precision layout: C logical channels stored as [hi C | lo C] per pixel (two fp16 planes,
+// value = hi + lo); rows of score matrices as [hi Tp | lo Tp].
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,6 +20,7 @@ enum DirectConvFlags : int {
 struct DirectConvParams {
   const void* in;       // 16-bit NHWC, channel stride in_cstride
   int N, H, W, Cin, in_cstride;
+  int in_lo, out_lo;    // high-precision layout: element offset of the lo plane inside a pixel (0 = plain 16-bit)
   const float* w;       // fp32 [ks*ks][Cin][Cout]
   const float* bias;    // fp32 [Cout] or null
   const void* res;      // 16-bit NHWC (out_cstride) or null
@@ -32,36 +35,37 @@ cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s);
 // scale / shift -> apply.  chunks = gn_chunks(N, HW) for every source of one normalisation.
 int gn_chunks(int N, long long HW);
 cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, int chunks, int Ctot, int coff,
-                     bool bf16, cudaStream_t s);
+                     bool bf16, cudaStream_t s, bool split = false);
 // one source of a (possibly concatenated) normalisation: partial sums [N][chunks][C][2]; the partials
 // come either from gn_stats or from the producing implicit-GEMM's epilogue (IgemmParams::stats).
 struct GnSrc { const float* partial; int chunks; int C; };
 cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const float* beta, int N, int Ctot,
                         int groups, long long HW, float eps, float* scale_shift /*[N][Ctot][2]*/, cudaStream_t s);
 cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* scale_shift, int Ctot,
-                     int coff, void* y, int y_cstride, bool silu, bool bf16, cudaStream_t s);
+                     int coff, void* y, int y_cstride, bool silu, bool bf16, cudaStream_t s, bool split = false);
 
 cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const float* gamma,
-                      const float* beta, float eps, bool bf16, cudaStream_t s);
+                      const float* beta, float eps, bool bf16, cudaStream_t s, bool split = false);
 // in-place softmax over the first T entries of each row (row stride Tp elements)
-cudaError_t softmax_rows(void* s_inout, long long rows, int T, int Tp, bool bf16, cudaStream_t s);
+cudaError_t softmax_rows(void* s_inout, long long rows, int T, int Tp, bool bf16, cudaStream_t s, bool split = false);
 // y = x + c0 + sigmoid(LN(x) . U + u0) . M     (U already carries LN gamma, u0 beta)
 cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, const float* U /*[h][C]*/,
                    const float* u0 /*[h]*/, const float* M /*[h][C]*/, const float* c0 /*[C]*/,
-                   float eps, bool bf16, cudaStream_t s);
+                   float eps, bool bf16, cudaStream_t s, bool split = false);
 cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16, cudaStream_t s);
-cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s);
+// split_c: 0, or the logical channel count C of a high-precision [hi C | lo C] tensor (n = pixels * C)
+cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s, int split_c = 0);
 cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C, bool bf16,
-                          cudaStream_t s);
+                          cudaStream_t s, bool split = false);
 // In-place softmax over each of `groups` consecutive runs of `n` columns of every row of x [rows, ld] (16-bit); columns
 // beyond groups*n are left untouched (zero padding of the general cross-attention score matrix).
-cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s);
+cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s, bool split = false);
 // F.interpolate(size=(OH,OW), mode="nearest") on 16-bit NHWC: src = min(floor(dst * in/out), in-1)  (the UNet's
 // Upsample2D with an explicit output size, when H/8 or W/8 is not a multiple of 8)
 cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s);
 // u8 / f16 / f32 NCHW [N,3,H,W] -> 16-bit NHWC8 (channels 3..7 zero); u8 is mapped x/255*2-1.
 cudaError_t preprocess_rgb(const void* in, int in_kind /*0 u8, 1 f16, 2 f32*/, void* out, int N, int H,
-                           int W, bool bf16, cudaStream_t s);
+                           int W, bool bf16, cudaStream_t s, bool split = false);
 // per-image (x - min) / (max - min) over HW fp32 values, in place; scratch: 2 uint32 per image.
 cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s);
 

@@ -23,7 +23,7 @@ _STATUS = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_MISSING", 3: "GP_ERR_NO_P
 
 class _Config(ctypes.Structure):
     _fields_ = [("device", c_int), ("dtype", c_int), ("readout", c_int), ("timestep", c_int),
-                ("use_cuda_graph", c_int)]
+                ("use_cuda_graph", c_int), ("precision", c_int)]
 
 
 _lib = None
@@ -92,7 +92,8 @@ def _check_free(st, what):
 class Engine:
     """One engine per (process, GPU).  Mirrors the C-ABI one to one."""
 
-    def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph="auto"):
+    def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph="auto",
+                 precision="default"):
         if not torch.cuda.is_available():
             raise RuntimeError("genpercept_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.L = lib()
@@ -100,7 +101,9 @@ class Engine:
         self.readout = readout
         self.device = torch.device("cuda", device)
         cfg = _Config(device, _gp_dtype(dtype), GP_READOUT_DPT if readout == "dpt" else GP_READOUT_VAE, timestep,
-                      2 if cuda_graph == "auto" else (1 if cuda_graph else 0))   # auto: graphs for small plans
+                      2 if cuda_graph == "auto" else (1 if cuda_graph else 0),   # auto: graphs for small plans
+                      {"default": 0, "high": 1}[precision])
+        self.precision = precision
         self.h = c_void_p()
         st = self.L.gp_create(byref(cfg), byref(self.h))
         if st != 0:

@@ -74,7 +74,7 @@ class GenPerceptPipeline:
     def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None,
                  default_denoising_steps: Optional[int] = 10, default_processing_resolution: Optional[int] = 768,
                  rgb_blending=False, customized_head=None, genpercept_pipeline=True, *, text_embed=None,
-                 torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None):
+                 torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None, precision=None):
         self.genpercept_pipeline = genpercept_pipeline
         if not genpercept_pipeline:
             raise NotImplementedError("only the one-step GenPercept mode (genpercept_pipeline=True) is built; "
@@ -92,13 +92,17 @@ class GenPerceptPipeline:
         self.rgb_blending = rgb_blending
         self.customized_head = customized_head
         self.text_embed = None
+        # run.py:273-281: fp32 unless --half_precision.  torch_dtype=float32 (the reference default) selects the
+        # engine's high-precision mode — every operand an fp16 (hi, lo) pair, three tensor-core passes, fp32
+        # accumulate: fp32-class results at ~3x the tensor work; float16 / bfloat16 select 16-bit storage.
         self.dtype = torch.float32 if torch_dtype is None else torch_dtype
-        if self.dtype == torch.float32:
-            logging.warning("genpercept_b200 computes in 16-bit storage / fp32 accumulate; using float16")
-            self.dtype = torch.float16
+        if precision is None:
+            precision = "high" if self.dtype == torch.float32 else "default"
+        self.precision = precision
+        storage = torch.bfloat16 if self.dtype == torch.bfloat16 else torch.float16
         self._timestep = int(fix_timesteps) if fix_timesteps else 1
-        self._engine = Engine(dtype=self.dtype, readout="dpt" if customized_head is not None else "vae",
-                              timestep=self._timestep, device=device, cuda_graph=cuda_graph)
+        self._engine = Engine(dtype=storage, readout="dpt" if customized_head is not None else "vae",
+                              timestep=self._timestep, device=device, cuda_graph=cuda_graph, precision=precision)
         self.device = self._engine.device
         unet_sd = dict(_as_state_dict(unet))
         vae_sd = W.remap_legacy_vae_keys(_as_state_dict(vae))

@@ -44,6 +44,10 @@ typedef struct {
   int timestep;          /* UNet timestep; 1 for GenPercept (ddim.py + scheduler beta=1), or
                             the reference's --fix_timesteps value                           */
   int use_cuda_graph;    /* 0 eager, 1 replay one captured CUDA graph per plan, 2 auto (small plans) */
+  int precision;         /* 0: 16-bit storage, fp32 accumulate (the reference's --half_precision class);
+                            1: high — every activation and weight is carried as an fp16 (hi, lo) pair and every
+                            contraction runs hi*hi + lo*hi + hi*lo on the tensor cores (fp32-class products,
+                            fp32 accumulate): the reference's default fp32 run (run.py:273-281)              */
 } gp_config;
 
 /* replaces: GenPerceptPipeline.__init__/from_pretrained model assembly (run.py:314-376) */
