@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["igemm.cu", "fattn.cu", "kernels.cu", "imgproc.cu", "builder.cu", "engine.cu"]
+SOURCES = ["igemm.cu", "igemm_patch.cu", "fattn.cu", "kernels.cu", "imgproc.cu", "builder.cu", "engine.cu"]
 LIB = os.path.join(HERE, "libgenpercept_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -131,8 +131,36 @@ static void finalize_or_throw(IgemmParams* p, const std::string& name) {
   if (err) throw GpError(GP_ERR_INVALID, name + ": " + err);
 }
 
+// The patch-resident kernel with the GroupNorm transform in its operand path (igemm_patch.cu) takes a convolution when:
+// 3x3 stride 1, ONE normalised source (channels % 64 == 0), at most one raw shortcut source, W % 128 == 0, and either the
+// staged epilogue (Cout % 64 == 0) or an fp32 map as output.  GP_NO_GN_FUSE=1 disables it (A/B switch).
+static bool gn_fusable(const ConvArgs& a, bool split) {
+  static const bool off = std::getenv("GP_NO_GN_FUSE") != nullptr || std::getenv("GP_NO_PATCH") != nullptr;
+  if (off || split || a.mode != 0 || a.ks != 3 || a.srcs.size() != 1 || a.sc.size() > 1) return false;
+  const T4& s = a.srcs[0];
+  if ((s.W % 128) || (s.C % 64) || (!a.sc.empty() && (a.sc[0].C % 64))) return false;
+  const int Cout = a.cout_valid > 0 ? a.cout_valid : a.out.C;
+  if (!a.out_f32 && (Cout != a.out.C || (Cout % 64))) return false;
+  if (a.flags & IG_GEGLU) return false;
+  return true;
+}
+
 void Builder::conv(const std::string& name, const ConvArgs& a) {
   GP_REQUIRE(!a.srcs.empty() && a.w != nullptr, name + ": bad conv args");
+  const bool gn_fused = a.gn != nullptr && gn_fusable(a, split_);
+  if (a.gn != nullptr && !gn_fused) {      // materialise GroupNorm(+SiLU)(concat(srcs)), then the plain convolution
+    int ctot = 0;
+    for (auto& s : a.srcs) ctot += s.C;
+    T4 tmp = alloc(a.srcs[0].N, a.srcs[0].H, a.srcs[0].W, ctot);
+    gn(a.gn_name, a.srcs, *a.gn, a.gn_groups, a.gn_eps, a.gn_silu, tmp);
+    ConvArgs b = a;
+    b.gn = nullptr;
+    b.srcs = {tmp};
+    conv(name, b);
+    release(tmp);
+    return;
+  }
+  if (gn_fused) gn_scale_shift(a.gn_name, a.srcs, *a.gn, a.gn_groups, a.gn_eps);
   const T4& s0 = a.srcs[0];
   const int N = s0.N, H = s0.H, W = s0.W;
   int Ho = H, Wo = W;
@@ -159,7 +187,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const int bn_pre = choose_bn(Cout, a.force_bn);
   const long long work_px = tokens_mode ? (long long)N * H * W
                                         : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
-  const int mt_pre = (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+  const int mt_pre = gn_fused ? ((bn_pre <= 128 && (H % 2) == 0) ? 2 : 1) : (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
                       (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr && !split_ &&   // measured slower than the direct GEGLU stores (r1g)
@@ -168,8 +196,8 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   // GP_STATS: 0 = never fuse the GroupNorm partial sums into conv epilogues, 1 = always (default), 2 = everywhere
   // except the patch-resident layers (whose main loop runs at the tensor-pipe limit, so the epilogue is critical)
   static const int stats_mode = std::getenv("GP_STATS") ? std::atoi(std::getenv("GP_STATS")) : 1;
-  const bool patch_eligible = a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && mt_pre == 2 && (W % 128) == 0 &&
-                              (H % 2) == 0 && !split_ && std::getenv("GP_NO_PATCH") == nullptr;
+  const bool patch_eligible = gn_fused || (staged && a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && mt_pre == 2 &&
+                                           (W % 128) == 0 && (H % 2) == 0 && !split_ && std::getenv("GP_NO_PATCH") == nullptr);
   bool emit_stats = a.want_stats && staged && !is_geglu && Cout <= 512 && stats_mode != 0 && !(stats_mode == 2 && patch_eligible) && !split_;
   if (emit_stats && tokens_mode && ((long long)H * W) % (128 * mt_pre) != 0) emit_stats = false;
   size_t stats_off = 0;
@@ -221,8 +249,9 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     p.gridW = (a.mode == 3) ? W : Wo;
     p.gridH = (a.mode == 3) ? H : Ho;
     // two accumulator tiles per CTA when the N tile is narrow and there is enough work to fill the GPU
-    p.MT = (p.BN <= 128 && (long long)p.gridW * p.gridH * N * (a.mode == 3 ? 4 : 1) >= 256LL * 148) ? 2 : 1;
-    choose_tile(p.gridW, p.gridH, 128 * p.MT, &p.TW, &p.TH, &p.tw_shift);
+    p.MT = mt_pre;
+    if (patch_eligible) { p.TW = 128; p.TH = p.MT; p.tw_shift = 7; }
+    else choose_tile(p.gridW, p.gridH, 128 * p.MT, &p.TW, &p.TH, &p.tw_shift);
     int nmap = 0;
     if (a.mode == 0 || a.mode == 3) {
       GP_REQUIRE(a.srcs.size() + a.sc.size() <= 4, name + ": too many sources");
@@ -350,12 +379,24 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     }
   }
   // patch-resident main loop for the wide-image, narrow-N 3x3 layers
-  if (staged && a.mode == 0 && a.ks == 3 && a.srcs.size() == 1 && a.sc.empty() && p.MT == 2 && p.TW == 128 && p.TH == 2 &&
-      (W % 128) == 0 && (H % 2) == 0 && !split_ && std::getenv("GP_NO_PATCH") == nullptr) {
+  if (patch_eligible) {
+    GP_REQUIRE(p.TW == 128 && p.TH == p.MT, name + ": patch tile");
     p.patch = 1;
     p.kc_count = ceil_div(s0.C, 64);
     check_cuda(make_tmap_a(&p.tmPatch, ptr(s0), s0.C, W, H, N, s0.C, (long long)W * s0.C, (long long)H * W * s0.C,
                            p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch");
+    p.tmPatch2 = p.tmPatch;
+    if (!a.sc.empty()) {
+      const T4& x = a.sc[0];
+      p.kc_sc = ceil_div(x.C, 64);
+      check_cuda(make_tmap_a(&p.tmPatch2, ptr(x), x.C, W, H, N, x.C, (long long)W * x.C, (long long)H * W * x.C,
+                             p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch (shortcut)");
+    }
+    if (gn_fused) {
+      p.gn_ss = gn_ss;
+      p.gn_C = s0.C;
+      p.gn_silu = a.gn_silu ? 1 : 0;
+    }
   }
   if (emit_stats) {
     p.stats = reinterpret_cast<float*>(raw_ptr(stats_off));
@@ -553,6 +594,54 @@ void Builder::attention(const std::string& name, const T4& l, const PackedW& wqk
                 split_ ? 2LL * C : 0);
   arena_.release(vt_off);
   release(qk);
+}
+
+void Builder::gn_scale_shift(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps) {
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  GP_REQUIRE(nw.C == ctot && ctot % groups == 0 && srcs.size() <= 2 && !srcs.empty(), name + ": GroupNorm channel mismatch");
+  const int N = srcs[0].N;
+  const long long HW = (long long)srcs[0].H * srcs[0].W;
+  const int chunks = gn_chunks(N, HW);
+  std::vector<size_t> own(srcs.size(), (size_t)-1);
+  std::vector<GnSrc> gs(srcs.size());
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    auto it = stats.find(srcs[i].off);
+    if (it != stats.end() && it->second.C == srcs[i].C) {
+      gs[i] = GnSrc{measuring_ ? nullptr : reinterpret_cast<const float*>(raw_ptr(it->second.off)), it->second.slots, srcs[i].C};
+    } else {
+      own[i] = arena_.alloc((size_t)N * chunks * srcs[i].C * 2 * sizeof(float));
+      gs[i] = GnSrc{measuring_ ? nullptr : reinterpret_cast<const float*>(raw_ptr(own[i])), chunks, srcs[i].C};
+    }
+  }
+  if (!measuring_) {
+    float* ss = gn_ss;
+    const bool bf = bf16_, sp = split_;
+    std::vector<const void*> xs;
+    std::vector<int> cs;
+    std::vector<bool> need;
+    int launches = 1;
+    double bytes = 0;
+    for (size_t i = 0; i < srcs.size(); ++i) {
+      xs.push_back(ptr(srcs[i]));
+      cs.push_back(srcs[i].C);
+      need.push_back(own[i] != (size_t)-1);
+      if (need[i]) { bytes += (double)srcs[i].bytes(); ++launches; }
+    }
+    const float* gamma = nw.gamma;
+    const float* beta = nw.beta;
+    push(name, launches, 0, bytes, [=](cudaStream_t s) {
+      cudaError_t e;
+      for (size_t i = 0; i < xs.size(); ++i) {
+        if (!need[i]) continue;
+        e = gn_stats(xs[i], N, HW, cs[i], const_cast<float*>(gs[i].partial), chunks, cs[i], 0, bf, s, sp);
+        if (e != cudaSuccess) return e;
+      }
+      return gn_finalize(gs.data(), (int)gs.size(), gamma, beta, N, ctot, groups, HW, eps, ss, s);
+    });
+  }
+  for (size_t i = 0; i < srcs.size(); ++i)
+    if (own[i] != (size_t)-1) arena_.release(own[i]);
 }
 
 void Builder::gn(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps,

@@ -448,27 +448,25 @@ struct gp_engine {
     std::vector<int> cs;
     for (auto& x : xs) { cin += x.C; cs.push_back(x.C); }
     const T4& x0 = xs[0];
-    T4 a = b.alloc(x0.N, x0.H, x0.W, cin);
-    b.gn(p + ".norm1", xs, norm_w(p + ".norm1"), 32, eps, true, a);
+    // norm1 -> SiLU -> conv1 and norm2 -> SiLU -> conv2: the normalisation is an attribute of the convolution (fused into
+    // its operand path where the patch-resident kernel applies, materialised by Builder::conv elsewhere)
     T4 h = b.alloc(x0.N, x0.H, x0.W, cout);
     {
       std::vector<float> tp;
       if (temb_on && !packed.count(p + ".conv1")) tp = temb_proj(p + ".time_emb_proj");
       ConvArgs c;
-      c.srcs = {a};
+      c.srcs = xs;
+      c.gn = &norm_w(p + ".norm1"); c.gn_name = p + ".norm1"; c.gn_eps = eps;
       c.w = &conv_w(p + ".conv1", {cin}, "", {}, tp.empty() ? nullptr : &tp);
       c.out = h;
       c.want_stats = true;     // feeds norm2
       b.conv(p + ".conv1", c);
     }
-    b.release(a);
-    T4 a2 = b.alloc(x0.N, x0.H, x0.W, cout);
-    b.gn(p + ".norm2", {h}, norm_w(p + ".norm2"), 32, eps, true, a2);
-    b.release(h);
     T4 out = b.alloc(x0.N, x0.H, x0.W, cout);
     {
       ConvArgs c;
-      c.srcs = {a2};
+      c.srcs = {h};
+      c.gn = &norm_w(p + ".norm2"); c.gn_name = p + ".norm2"; c.gn_eps = eps;
       c.out = out;
       c.want_stats = true;     // resnet outputs feed the next GroupNorm (norm1 / transformer norm / conv_norm_out)
       if (cin != cout) {
@@ -480,7 +478,7 @@ struct gp_engine {
       }
       b.conv(p + ".conv2", c);
     }
-    b.release(a2);
+    b.release(h);
     return out;
   }
 
@@ -623,9 +621,6 @@ struct gp_engine {
       }
     }
     x = vae_mid(b, e + ".mid_block", x);
-    T4 a = b.alloc(x.N, x.H, x.W, 512);
-    b.gn(e + ".conv_norm_out", {x}, norm_w(e + ".conv_norm_out"), 32, 1e-6f, true, a);
-    b.release(x);
     // conv_out (512->8) o quant_conv (8->8), mean channels, * 0.18215  ->  one 3x3 conv 512->4 (App. C.2)
     if (!packed.count("vae.encoder.tail")) {
       const HostT &w = T(e + ".conv_out.weight"), &bb = T(e + ".conv_out.bias"), &q = T("vae.quant_conv.weight"), &qb = T("vae.quant_conv.bias");
@@ -645,9 +640,13 @@ struct gp_engine {
       for (int r = 0; r < 9; ++r) { SegSpec sg; sg.C = 512; sg.terms.push_back(Term{f.data() + r, 512 * 9, 9, 1.f}); segs.push_back(sg); }
       packed.emplace("vae.encoder.tail", pack({segs}, 8, bias));
     }
-    T4 lat = b.alloc(a.N, a.H, a.W, 8);
-    { ConvArgs c; c.srcs = {a}; c.w = &packed.at("vae.encoder.tail"); c.out = lat; b.conv("vae.encoder.tail", c); }
-    b.release(a);
+    T4 lat = b.alloc(x.N, x.H, x.W, 8);
+    {
+      ConvArgs c; c.srcs = {x}; c.w = &packed.at("vae.encoder.tail"); c.out = lat;
+      c.gn = &norm_w(e + ".conv_norm_out"); c.gn_name = e + ".conv_norm_out"; c.gn_eps = 1e-6f;
+      b.conv("vae.encoder.tail", c);
+    }
+    b.release(x);
     return lat;
   }
 
@@ -757,9 +756,6 @@ struct gp_engine {
       b.release(cur);
       return;
     }
-    T4 a = b.alloc(cur.N, cur.H, cur.W, 320);
-    b.gn(u + ".conv_norm_out", {cur}, norm_w(u + ".conv_norm_out"), 32, 1e-5f, true, a);
-    b.release(cur);
     // conv_out, DDIM(beta=1) x0 = -v, /0.18215, post_quant_conv  ->  one 3x3 conv 320->4 (App. C.3)
     if (!packed.count("unet.tail")) {
       const HostT &w = T(u + ".conv_out.weight"), &bb = T(u + ".conv_out.bias"), &pq = T("vae.post_quant_conv.weight"), &pb = T("vae.post_quant_conv.bias");
@@ -780,8 +776,12 @@ struct gp_engine {
       for (int r = 0; r < 9; ++r) { SegSpec sg; sg.C = 320; sg.terms.push_back(Term{f.data() + r, 320 * 9, 9, 1.f}); segs.push_back(sg); }
       packed.emplace("unet.tail", pack({segs}, 8, bias));
     }
-    { ConvArgs c; c.srcs = {a}; c.w = &packed.at("unet.tail"); c.out = *z_out; b.conv("unet.tail", c); }
-    b.release(a);
+    {
+      ConvArgs c; c.srcs = {cur}; c.w = &packed.at("unet.tail"); c.out = *z_out;
+      c.gn = &norm_w(u + ".conv_norm_out"); c.gn_name = u + ".conv_norm_out"; c.gn_eps = 1e-5f;
+      b.conv("unet.tail", c);
+    }
+    b.release(cur);
   }
 
   // decode_pred + clip + shift: genpercept_pipeline.py:507-526, :470-472
@@ -806,9 +806,6 @@ struct gp_engine {
         x = y;
       }
     }
-    T4 a = b.alloc(x.N, x.H, x.W, 128);
-    b.gn(d + ".conv_norm_out", {x}, norm_w(d + ".conv_norm_out"), 32, 1e-6f, true, a);
-    b.release(x);
     // 3-channel (normal / seg) and channel-mean (depth / matting / dis / disparity) variants
     if (!packed.count("vae.decoder.tail1")) {
       const HostT &w = T(d + ".conv_out.weight"), &bb = T(d + ".conv_out.bias");
@@ -824,17 +821,18 @@ struct gp_engine {
     for (int variant : {1, 3}) {
       b.variant = variant;
       ConvArgs c;
-      c.srcs = {a};
+      c.srcs = {x};
+      c.gn = &norm_w(d + ".conv_norm_out"); c.gn_name = d + ".conv_norm_out"; c.gn_eps = 1e-6f;
       c.w = variant == 1 ? &packed.at("vae.decoder.tail1") : &packed.at(d + ".conv_out");
       c.out_f32 = out_f32;
       c.cout_valid = variant;
       c.flags = IG_AFFINE_CLAMP01;
-      T4 shape = a;   // only N/H/W are consulted for fp32 outputs
+      T4 shape = x;   // only N/H/W are consulted for fp32 outputs
       c.out = shape;
       b.conv("vae.decoder.tail" + std::to_string(variant), c);
     }
     b.variant = 0;
-    b.release(a);
+    b.release(x);
   }
 
   // DPTNeckHeadForUnetAfterUpsampleIdentity (dpt_head.py:530-546), then per-image min-max (:482, F12)
@@ -1379,6 +1377,62 @@ gp_status gp_groupnorm(int dtype, const void* x, int N, int H, int W, int C, int
     Builder b(te.e.bf16, false, reinterpret_cast<uint8_t*>(arena));
     b.gn_ss = ss;
     b.gn("gp_groupnorm", {b.external(x, N, H, W, C)}, nw, groups, eps, silu != 0, b.external(y, N, H, W, C));
+    run_all(b, s);
+    GP_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+gp_status gp_gn_conv3x3(int dtype, const void* x, int N, int H, int W, int Cin, int groups, const float* gamma_host,
+                        const float* beta_host, float eps, int silu, const float* w_host, const float* bias_host, int Cout,
+                        const void* sc_x, int Csc, const float* sc_w_host, const float* sc_b_host, const void* residual,
+                        void* y, int out_f32, void* stream) {
+  return guarded_free([&]() {
+    GP_REQUIRE(x && w_host && y && gamma_host && beta_host, "gp_gn_conv3x3: bad arguments");
+    GP_REQUIRE(dtype == GP_F16 || dtype == GP_BF16, "gp_gn_conv3x3: dtype must be f16/bf16");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    TempEngine te(dtype);
+    auto put = [&](const char* k, std::vector<int64_t> shape, const float* d) {
+      HostT t;
+      t.shape = shape;
+      t.d.assign(d, d + t.numel());
+      te.e.host[k] = std::move(t);
+    };
+    put("t.weight", {Cout, Cin, 3, 3}, w_host);
+    std::vector<float> zb(Cout, 0.f);
+    put("t.bias", {Cout}, bias_host ? bias_host : zb.data());
+    if (sc_x) {
+      GP_REQUIRE(sc_w_host != nullptr, "gp_gn_conv3x3: shortcut weights missing");
+      put("s.weight", {Cout, Csc, 1, 1}, sc_w_host);
+      put("s.bias", {Cout}, sc_b_host ? sc_b_host : zb.data());
+    }
+    NormW nw;
+    nw.C = Cin;
+    nw.gamma = te.e.upload(std::vector<float>(gamma_host, gamma_host + Cin));
+    nw.beta = te.e.upload(std::vector<float>(beta_host, beta_host + Cin));
+    float* ss = te.e.upload(std::vector<float>((size_t)N * Cin * 2, 0.f));
+    const PackedW& pw = sc_x ? te.e.conv_w("t", {Cin}, "s", {Csc}) : te.e.conv_w("t", {Cin});
+    auto emit = [&](Builder& b) {
+      ConvArgs c;
+      c.srcs = {b.external(x, N, H, W, Cin)};
+      c.gn = &nw; c.gn_name = "gn"; c.gn_groups = groups; c.gn_eps = eps; c.gn_silu = silu != 0;
+      c.w = &pw;
+      T4 res;
+      if (sc_x) c.sc = {b.external(sc_x, N, H, W, Csc)};
+      if (residual) { res = b.external(residual, N, H, W, Cout); c.res1 = &res; }
+      if (out_f32) { c.out_f32 = reinterpret_cast<float*>(y); c.cout_valid = Cout; c.out = b.external(x, N, H, W, Cin); }
+      else c.out = b.external(y, N, H, W, Cout);
+      b.conv("gp_gn_conv3x3", c);
+    };
+    void* arena = nullptr;
+    {
+      Builder m(te.e.bf16, true, nullptr);
+      emit(m);
+      GP_CUDA(cudaMalloc(&arena, m.arena_bytes() + 1024));
+      te.e.dev_allocs.push_back(arena);
+    }
+    Builder b(te.e.bf16, false, reinterpret_cast<uint8_t*>(arena));
+    b.gn_ss = ss;
+    emit(b);
     run_all(b, s);
     GP_CUDA(cudaStreamSynchronize(s));
   });

@@ -101,6 +101,14 @@ struct ConvArgs {
   float* out_f32 = nullptr;   // fp32 NCHW destination [N, cout_valid, Ho, Wo]
   int force_bn = 0;
   bool want_stats = false;    // let the epilogue emit GroupNorm partial sums of `out` (consumed by Builder::gn)
+  // GroupNorm(+SiLU) over concat(srcs) in front of the convolution (norm1 / norm2 / conv_norm_out of the diffusers
+  // blocks).  Where the patch-resident kernel applies, it is fused into the operand path (igemm_patch.cu); elsewhere
+  // Builder::conv materialises the normalised tensor with Builder::gn and convolves that.
+  const NormW* gn = nullptr;
+  std::string gn_name;
+  int gn_groups = 32;
+  float gn_eps = 1e-6f;
+  bool gn_silu = true;
 };
 
 class Builder {
@@ -122,6 +130,8 @@ class Builder {
                      int T, int heads, int d, const float* pv_bias, const T4& out, long long qk_lo = 0);
   void gn(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps, bool silu,
           const T4& out);
+  // statistics -> per-(image, channel) scale / shift in gn_ss (the first half of gn(); the apply pass is the caller's)
+  void gn_scale_shift(const std::string& name, const std::vector<T4>& srcs, const NormW& nw, int groups, float eps);
   void ln(const std::string& name, const T4& x, const NormW& nw, float eps, const T4& out);
   void xattn(const std::string& name, const T4& x, const XattnW& w, float eps, const T4& out);
   void geglu_op(const std::string& name, const T4& in, const T4& out);

@@ -93,16 +93,25 @@ struct IgemmParams {
   // look-ups per warp request (ncu r1k: 58 % tensor pipe with a residual vs 92 % without, same layer).
   int res_tma;
   CUtensorMap tmRes[kMaxClasses];
-  // Patch-resident main loop (3x3 stride-1, one source, TW = 128, MT = 2, staged epilogue): per
+  // Patch-resident main loop (igemm_patch.cu; 3x3 stride-1, one source, TW = 128, TH = MT = 1 or 2): per
   // 64-channel K chunk ONE (TH+2) x (TW+2) halo patch is loaded and all nine taps are fed from it by
   // row-offset descriptors (tap (dy,dx) starts (h+dy+1)*(TW+2) + dx+1 rows into the patch), instead of
   // nine shifted boxes.  Cuts the activation L2->SM traffic 9 -> 2.03 reads per element: the narrow-N
   // (Cout = 128) layers are bound by exactly that traffic (~42 B/clk/SM of unique data).
   int patch;
   int kc_count;                  // 64-channel K chunks per tap (packed weights are tap-major, kc_count*64 wide per tap)
+  int kc_sc;                     // extra centre-tap-only chunks from tmPatch2 (fused 1x1 shortcut over the raw block input)
   int a_slot_bytes;              // bytes reserved per patch slot (2 slots), multiple of 1024
   CUtensorMap tmPatch;           // (C, W, H, N) view of the source, box (64, TW+2, TH+2, 1)
+  CUtensorMap tmPatch2;          // same box over the shortcut source
+  // GroupNorm(+SiLU) of the patch source applied in shared memory before the MMA reads it (patch mode only):
+  // y = silu(x * scale + shift), (scale, shift) = gn_ss[(image * gn_C + channel) * 2 + {0, 1}] (gn_finalize's output).
+  const float* gn_ss;            // null: the source is used as it is
+  int gn_C;                      // channels of the normalised tensor (= the patch source's)
+  int gn_silu;
 };
+
+cudaError_t igemm_patch_launch(const IgemmParams& p, int grid, cudaStream_t stream);   // igemm_patch.cu
 
 int igemm_grid(const IgemmParams& p);   // CTAs that igemm_launch will use for p (after igemm_finalize)
 

@@ -1,0 +1,293 @@
+// Patch-resident tcgen05 implicit GEMM for 3x3 stride-1 convolutions over wide images (W % 128 == 0), with the
+// producer-side GroupNorm(+SiLU) applied to the operand ON ITS WAY to the tensor core.
+//
+// Per 64-channel K chunk ONE (TH+2) x 130 pixel halo patch of the source lands in shared memory (a single TMA box,
+// image borders zero-filled) and all nine filter taps are fed from it by row-offset SWIZZLE_128B descriptors: tap
+// (dy,dx) of image row h starts ((h+dy+1)*130 + dx+1) rows into the patch (scripts/exp_baseoffset.cu: any 128-byte
+// row is a valid descriptor start because the swizzle is a function of the absolute shared-memory address).
+// Activation traffic L2 -> SM drops from 9 to (TH+2)*130 / (TH*128) reads per element.
+//
+// GroupNorm fusion (reference call sites: every `norm1 -> SiLU -> conv1` /
+// `norm2 -> SiLU -> conv2` / `conv_norm_out -> SiLU -> conv_out` of the diffusers VAE blocks that
+// /root/reference/genpercept/genpercept_pipeline.py:500,521 drive): the statistics of the source tensor come from
+// its producer's epilogue (gn_finalize turns them into one (scale, shift) pair per (image, channel)); a transform
+// warpgroup rewrites each landed patch in place, y = silu(x * scale + shift), leaving the zero-filled halo pixels
+// outside the image at zero (the convolution pads the NORMALISED tensor with zeros), and only then hands the patch to
+// the MMA issuers.  The normalised tensor never exists in HBM: one 2-byte read + one 2-byte write per element and
+// one kernel launch less per GroupNorm.
+//
+// Extra K chunks for a fused 1x1 shortcut (ResnetBlock2D.conv_shortcut over the RAW block input): centre tap only,
+// loaded through a second tensor map and passed through the transform stage untouched.
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent; registers re-balanced with setmaxnreg):
+//   warps 0..3   : epilogue (staged + TMA store, or direct for fp32 maps) — same code as the tap-streaming kernel
+//   warp 4       : patch producer (TMA)           warp 7 : weight producer (TMA, one box per (chunk, tap))
+//   warps 5 (,6) : MMA issuers, one per image row of the tile (MT = TH = 1 or 2); warp 6 also owns the TMEM allocation
+//   warps 8..11  : operand transform (GroupNorm scale/shift + SiLU in place, or pass-through)
+#include <cstdlib>
+
+#include "igemm_common.cuh"
+
+namespace gp {
+
+namespace {
+
+constexpr int kPatchThreads = 384;
+constexpr int kPW = kBM + 2;      // patch width in pixels (TW = 128)
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ float silu_tanh(float x) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (kernels.cu silu_f)
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.BN * 128;
+  const int stages = p.stages;                       // depth of the weight ring
+  uint8_t* sB = smem + 2 * p.a_slot_bytes;
+  uint8_t* stg_base = sB + stages * b_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));
+  uint64_t* a_ready = a_full + 2;
+  uint64_t* a_empty = a_ready + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + stages;
+  uint64_t* tfull_bar = b_empty + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  float* sacc = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  const int prows = (p.TH + 2) * kPW;                // pixels (= 128-byte rows) of a patch
+  const uint32_t patch_bytes = (uint32_t)prows * 128;
+  const int kc_all = p.kc_count + p.kc_sc;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmPatch);
+    tma_prefetch_desc(&p.tmPatch2);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 128);                   // the transform warpgroup
+      mbar_init(&a_empty[i], p.MT);                  // one tcgen05.commit per MMA issuer
+    }
+    for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 6) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================================================================== epilogue
+    setmaxnreg_inc<232>();
+    if (p.tma_store) epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    else epilogue_direct<BF16>(p, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  } else if (warp < 8) {
+    setmaxnreg_dec<72>();
+    if (warp == 4) {
+      // =================================================================== patch producer
+      const bool leader = elect_one();
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int x0 = t.tx * p.TW - 1, y0 = t.ty * p.TH - 1;
+        for (int kc = 0; kc < kc_all; ++kc) {
+          const bool main = kc < p.kc_count;
+          mbar_wait(&a_empty[slot], phase ^ 1, 1);
+          if (leader) {
+            mbar_expect_tx(&a_full[slot], patch_bytes);
+            tma_load_4d(smem + slot * p.a_slot_bytes, main ? &p.tmPatch : &p.tmPatch2, &a_full[slot],
+                        (main ? kc : kc - p.kc_count) * kBK, x0, y0, t.z1);
+          }
+          __syncwarp();
+          if (++slot == 2) { slot = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 7) {
+      // =================================================================== weight producer
+      const bool leader = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int b_row = t.n_tile * p.BN;
+        for (int kc = 0; kc < kc_all; ++kc) {
+          const bool main = kc < p.kc_count;
+          const int ntap = main ? 9 : 1;
+          for (int tap = 0; tap < ntap; ++tap) {
+            // packed weights: [tap][main chunk] ... then the shortcut chunks
+            const int kblk = main ? tap * p.kc_count + kc : 9 * p.kc_count + (kc - p.kc_count);
+            mbar_wait(&b_empty[stage], phase ^ 1, 5);
+            if (leader) {
+              mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+              tma_load_3d(sB + stage * b_bytes, &p.tmB, &b_full[stage], kblk * kBK, b_row, 0);
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp - 5 < p.MT) {
+      // =================================================================== MMA issuers (one per image row h)
+      const bool leader = elect_one();
+      const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
+      const int h = warp - 5;
+      int slot = 0, stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tap_off[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((p.seg[0][tap].dy + 1 + h) * kPW + p.seg[0][tap].dx + 1) * 128;
+      const int centre_off = ((1 + h) * kPW + 1) * 128;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride + h * 128;
+        for (int kc = 0; kc < kc_all; ++kc) {
+          mbar_wait(&a_ready[slot], a_phase, 3);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(smem + slot * p.a_slot_bytes);
+          if (kc < p.kc_count) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_full[stage], b_phase, 6);
+              tc_fence_after();
+              const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * b_bytes));
+              if (leader) {
+                const uint64_t a_desc = make_sw128_kmajor_desc(patch + tap_off[tap]);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) ? 1u : 0u);
+                umma_commit(&b_empty[stage]);
+              }
+              __syncwarp();
+              if (++stage == stages) { stage = 0; b_phase ^= 1; }
+            }
+          } else {                                   // shortcut chunk: centre tap only (kc >= 1 here, always accumulate)
+            mbar_wait(&b_full[stage], b_phase, 6);
+            tc_fence_after();
+            const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(sB + stage * b_bytes));
+            if (leader) {
+              const uint64_t a_desc = make_sw128_kmajor_desc(patch + centre_off);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+              umma_commit(&b_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; b_phase ^= 1; }
+          }
+          if (leader) umma_commit(&a_empty[slot]);
+          __syncwarp();
+          if (++slot == 2) { slot = 0; a_phase ^= 1; }
+        }
+        if (leader) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================================================================== operand transform (warps 8..11)
+    setmaxnreg_dec<104>();
+    const int tt = threadIdx.x - 256;                // 0..127
+    const int cpos = tt & 7;                         // 16-byte position inside the 128-byte row
+    const int rbase = tt >> 3;                       // rows rbase, rbase + 16, ...
+    // SWIZZLE_128B: position = logical 16-byte chunk ^ (row & 7); rows advance by 16, so (row & 7) is fixed per thread
+    const int jlog = cpos ^ (rbase & 7);             // this thread's logical channel group (8 channels) in every chunk
+    const bool do_gn = p.gn_ss != nullptr;
+    const bool do_silu = p.gn_silu != 0;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int x0 = t.tx * p.TW - 1, y0 = t.ty * p.TH - 1;
+      const float* ssn = p.gn_ss + (long long)t.z1 * p.gn_C * 2;
+      for (int kc = 0; kc < kc_all; ++kc) {
+        const bool xf = do_gn && kc < p.kc_count;
+        float sc[8], sh[8];
+        if (xf) {                                    // fetched before the patch lands
+          const float4* sp = reinterpret_cast<const float4*>(ssn + (kc * kBK + jlog * 8) * 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 a = __ldg(sp + e);
+            sc[2 * e] = a.x; sh[2 * e] = a.y; sc[2 * e + 1] = a.z; sh[2 * e + 1] = a.w;
+          }
+        }
+        mbar_wait(&a_full[slot], phase, 8);
+        if (xf) {
+          const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
+          int py = 0, px = rbase;                    // rbase < 16 < kPW
+          for (int r = rbase; r < prows; r += 16) {
+            const bool inside = (unsigned)(y0 + py) < (unsigned)p.gridH && (unsigned)(x0 + px) < (unsigned)p.gridW;
+            if (inside) {
+              const uint32_t addr = base + r * 128;
+              uint32_t w[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = fmaf(cvt16<BF16>((uint16_t)(w[e] & 0xFFFF)), sc[2 * e], sh[2 * e]);
+                float b = fmaf(cvt16<BF16>((uint16_t)(w[e] >> 16)), sc[2 * e + 1], sh[2 * e + 1]);
+                if (do_silu) { a = silu_tanh(a); b = silu_tanh(b); }
+                w[e] = pack16<BF16>(a, b);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
+            px += 16;
+            if (px >= kPW) { px -= kPW; ++py; }
+          }
+          fence_proxy_async_shared();                // generic-proxy writes -> visible to the tensor core's reads
+        }
+        mbar_arrive(&a_ready[slot]);
+        if (++slot == 2) { slot = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    __syncwarp();          // reconverge before the .aligned dealloc
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+cudaError_t igemm_patch_launch(const IgemmParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_patch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(igemm_patch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  if (p.flags & IG_BF16)
+    igemm_patch_kernel<true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+  else
+    igemm_patch_kernel<false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace gp

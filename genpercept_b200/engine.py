@@ -61,6 +61,9 @@ def lib():
                             c_void_p, c_int, c_void_p, c_int, c_void_p]
     L.gp_groupnorm.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                c_int, c_void_p, c_void_p]
+    L.gp_gn_conv3x3.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p]
     L.gp_layernorm.argtypes = [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]
     L.gp_attention.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                c_void_p]
@@ -239,6 +242,25 @@ def groupnorm(x_nhwc, groups, gamma, beta, eps, silu):
                             c_void_p(g.data_ptr()), c_void_p(b.data_ptr()), eps, 1 if silu else 0,
                             c_void_p(y.data_ptr()), _stream_ptr())
     _check_free(st, "gp_groupnorm")
+    return y
+
+
+def gn_conv3x3(x_nhwc, groups, gamma, beta, eps, silu, w, bias=None, sc_x=None, sc_w=None, sc_b=None, residual=None,
+               out_f32=False):
+    """GroupNorm(+SiLU) -> 3x3 conv (+ 1x1 shortcut over raw sc_x, + residual) through gp_gn_conv3x3."""
+    N, H, W, Cin = x_nhwc.shape
+    Cout = w.shape[0]
+    f = lambda t: None if t is None else t.detach().float().cpu().contiguous()
+    g, b_, w_, bias_, scw, scb = f(gamma), f(beta), f(w), f(bias), f(sc_w), f(sc_b)
+    pp = lambda t: None if t is None else c_void_p(t.data_ptr())
+    if out_f32:
+        y = torch.zeros((N, Cout, H, W), dtype=torch.float32, device=x_nhwc.device)
+    else:
+        y = torch.zeros((N, H, W, Cout), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    st = lib().gp_gn_conv3x3(_gp_dtype(x_nhwc.dtype), pp(x_nhwc), N, H, W, Cin, groups, pp(g), pp(b_), eps, 1 if silu else 0,
+                             pp(w_), pp(bias_), Cout, pp(sc_x), 0 if sc_x is None else sc_x.shape[-1], pp(scw), pp(scb),
+                             pp(residual), pp(y), 1 if out_f32 else 0, _stream_ptr())
+    _check_free(st, "gp_gn_conv3x3")
     return y
 
 

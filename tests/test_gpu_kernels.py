@@ -136,6 +136,57 @@ def test_groupnorm(shape, groups, silu):
     _check(f"groupnorm {shape} silu={silu}", y.permute(0, 3, 1, 2), ref)
 
 
+@pytest.mark.parametrize("case", [
+    dict(N=1, H=64, W=128, Cin=128, Cout=128),                     # patch kernel, two image rows per tile (MT = 2)
+    dict(N=2, H=16, W=256, Cin=128, Cout=256),                     # BN = 256: one row per tile (MT = 1); per-image statistics
+    dict(N=1, H=8, W=128, Cin=64, Cout=512),                       # two N tiles over the same transformed patch
+    dict(N=1, H=5, W=128, Cin=64, Cout=64),                        # odd height: MT = 1 with a narrow N tile
+    dict(N=1, H=32, W=128, Cin=128, Cout=128, Csc=256),            # + fused 1x1 shortcut over the raw block input
+    dict(N=1, H=16, W=384, Cin=256, Cout=256, Csc=512),            # same with BN = 256, three tiles per image row
+    dict(N=1, H=32, W=128, Cin=128, Cout=128, residual=True),      # + identity residual
+    dict(N=2, H=32, W=256, Cin=128, Cout=1, out_f32=True),         # conv_norm_out -> conv_out (channel mean) -> fp32 map
+    dict(N=1, H=32, W=128, Cin=128, Cout=3, out_f32=True),
+    dict(N=1, H=24, W=96, Cin=128, Cout=128),                      # W % 128 != 0: GroupNorm pass + tap-streaming conv
+    dict(N=1, H=16, W=128, Cin=128, Cout=128, silu=False),
+])
+def test_groupnorm_fused_into_conv3x3(case):
+    """GroupNorm(32)+SiLU applied in the convolution's operand path (igemm_patch.cu) against F.group_norm -> F.silu ->
+    F.conv2d on the same 16-bit inputs.  The fused kernel rounds the normalised operand to 16 bit exactly like the
+    two-pass form does (it is the same arithmetic on a patch in shared memory), so the single-op bound applies."""
+    from genpercept_b200 import engine as E
+    _setup()
+    N, H, W, Cin, Cout = (case[k] for k in ("N", "H", "W", "Cin", "Cout"))
+    Csc, silu = case.get("Csc"), case.get("silu", True)
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = (_rand((N, Cin, H, W), g).float() * 1.5 + 0.3 * torch.randn((N, Cin, 1, 1), generator=g)).half()
+    gamma = 1 + 0.1 * torch.randn((Cin,), generator=g)
+    beta = 0.1 * torch.randn((Cin,), generator=g)
+    w = _rand((Cout, Cin, 3, 3), g, 1.0 / (Cin * 9) ** 0.5).float()
+    b = torch.randn((Cout,), generator=g) * 0.1
+    a = F.group_norm(x.cuda().float(), 32, gamma.cuda(), beta.cuda(), 1e-6)
+    if silu:
+        a = F.silu(a)
+    ref = F.conv2d(a.half().float(), w.cuda(), b.cuda(), padding=1)
+    sc_x = sc_w = sc_b = res = None
+    if Csc:
+        sc = _rand((N, Csc, H, W), g)
+        sc_w = _rand((Cout, Csc, 1, 1), g, 1.0 / Csc ** 0.5).float()
+        sc_b = torch.randn((Cout,), generator=g) * 0.1
+        ref = ref + F.conv2d(sc.cuda().float(), sc_w.cuda(), sc_b.cuda())
+        sc_x = E._nhwc(sc.cuda())
+    if case.get("residual"):
+        r = _rand((N, Cout, H, W), g)
+        ref = ref + r.cuda().float()
+        res = E._nhwc(r.cuda())
+    y = E.gn_conv3x3(E._nhwc(x.cuda()), 32, gamma, beta, 1e-6, silu, w, b, sc_x=sc_x, sc_w=sc_w, sc_b=sc_b, residual=res,
+                     out_f32=case.get("out_f32", False))
+    torch.cuda.synchronize()
+    got = y if case.get("out_f32") else y.permute(0, 3, 1, 2)
+    # the normalised operand is rounded to fp16 before the MMA in both implementations, but with tanh.approx inside
+    # SiLU: 2^-11 relative on operands of magnitude ~1 over K = 9 Cin terms
+    _check(f"gn+conv {case}", got, ref, rel=3e-3, abs_=2e-3)
+
+
 @pytest.mark.parametrize("tokens,C", [(100, 320), (64, 640), (33, 1280)])
 def test_layernorm(tokens, C):
     from genpercept_b200 import engine as E
