@@ -383,19 +383,21 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     GP_REQUIRE(p.TW == 128 && p.TH == p.MT, name + ": patch tile");
     p.patch = 1;
     p.kc_count = ceil_div(s0.C, 64);
+    // one TMA box per image row of the patch (igemm_patch.cu): box (64 channels, 130 pixels, 1 row, 1 image)
     check_cuda(make_tmap_a(&p.tmPatch, ptr(s0), s0.C, W, H, N, s0.C, (long long)W * s0.C, (long long)H * W * s0.C,
-                           p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch");
+                           p.TW + 2, 1, bf16_), name + ": tmap patch");
     p.tmPatch2 = p.tmPatch;
     if (!a.sc.empty()) {
       const T4& x = a.sc[0];
       p.kc_sc = ceil_div(x.C, 64);
       check_cuda(make_tmap_a(&p.tmPatch2, ptr(x), x.C, W, H, N, x.C, (long long)W * x.C, (long long)H * W * x.C,
-                             p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch (shortcut)");
+                             p.TW + 2, 1, bf16_), name + ": tmap patch (shortcut)");
     }
     if (gn_fused) {
       p.gn_ss = gn_ss;
       p.gn_C = s0.C;
-      p.gn_silu = a.gn_silu ? 1 : 0;
+      static const bool tanh32 = std::getenv("GP_PATCH_TANH32") != nullptr;     // A/B switch
+      p.gn_silu = a.gn_silu ? (tanh32 ? 2 : 1) : 0;
     }
   }
   if (emit_stats) {
@@ -416,6 +418,13 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
       cudaError_t e = cudaMemsetAsync(sp, 0, stats_bytes, s);
       if (e != cudaSuccess) return e;
       return igemm_launch(p, s);
+    });
+  } else if (a.out_f32 && out_slot) {
+    float** slot = out_slot;
+    push(name, 1, flops, bytes, [p, slot](cudaStream_t s) {
+      IgemmParams q = p;
+      q.out = *slot;
+      return igemm_launch(q, s);
     });
   } else {
     push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
@@ -781,8 +790,14 @@ void Builder::direct(const std::string& name, const T4& in, int cin, const Direc
   else { p.out = ptr(out); p.out_cstride = (int)out.ps(); p.out_lo = split_ ? out.C : 0; }
   const bool bf = bf16_;
   const double flops = 2.0 * p.N * p.Ho * p.Wo * (double)p.Cout * cin * w.ks * w.ks;
+  float** slot = out_f32 ? out_slot : nullptr;
   push(name, 1, flops, (double)in.bytes() + (double)p.N * p.Ho * p.Wo * p.Cout * (out_f32 ? 4 : 2),
-       [p, bf](cudaStream_t s) { return direct_conv(p, bf, s); });
+       [p, bf, slot](cudaStream_t s) {
+         if (!slot) return direct_conv(p, bf, s);
+         DirectConvParams q = p;
+         q.out = *slot;
+         return direct_conv(q, bf, s);
+       });
 }
 
 }  // namespace gp

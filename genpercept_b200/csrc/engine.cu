@@ -78,8 +78,12 @@ struct Plan {
   size_t arena_bytes = 0;
   std::vector<Op> ops;
   std::map<std::string, Kept> kept;
-  void* in_staging = nullptr;       // raw user input copy [B,3,H,W] (<= 4 bytes/elt)
-  float* out_f32 = nullptr;         // [B,3,H,W]
+  void* in_staging = nullptr;       // raw user input copy [B,3,H,W] (<= 4 bytes/elt), host inputs only
+  float* out_f32 = nullptr;         // [B,3,outH,outW]: the plan's own result buffer (graph replay, host outputs, stage runs)
+  float* out_dst = nullptr;         // where the final kernels write THIS launch (the caller's device buffer or out_f32);
+                                    // read by the ops at launch time through Builder::out_slot
+  int outH = 0, outW = 0;           // result extent: 8 * floor(H/8) (VAE readout), 64 * ceil-pyramid (DPT readout)
+  uint64_t last_used = 0;
   std::map<int, cudaGraphExec_t> graphs;   // by out_channels
   double igemm_flops = 0;
   int eager_runs = 0;                       // the first pass runs eagerly (kernel attributes, lazy init), then graphs
@@ -103,7 +107,17 @@ struct gp_engine {
   std::unordered_map<std::string, DirectW> directs;
   std::vector<void*> dev_allocs;
   size_t weight_bytes = 0;
-  std::vector<float> temb;   // [1280] time embedding for cfg.timestep
+  float* pq_dev = nullptr;   // vae.post_quant_conv: [16] weight + [4] bias, fp32 on the device
+  std::vector<float> temb;   // [1280] time embedding for the current timestep
+  // Per-call fix_timesteps (genpercept_pipeline.py:405-408): the timestep only enters through
+  // conv1.bias + time_emb_proj(silu(emb(t))) of the 22 UNet ResNets, so changing it re-folds those biases in place
+  // (the device bias buffers keep their addresses: every plan and captured graph sees the new values).
+  struct TembLayer { std::string key; std::vector<float> w, b, conv_bias; float* dev_bias = nullptr; int cout = 0; };
+  std::vector<TembLayer> temb_layers;
+  std::vector<float> te_w1, te_b1, te_w2, te_b2;
+  std::map<int, std::vector<std::vector<float>>> temb_cache;   // timestep -> folded bias per layer
+  int cur_timestep = 0;
+  uint64_t use_clock = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
   Plan* cur = nullptr;
 
@@ -389,10 +403,18 @@ struct gp_engine {
 
   void compute_temb() {
     if (!temb.empty()) return;
-    const HostT &w1 = T("unet.time_embedding.linear_1.weight"), &b1 = T("unet.time_embedding.linear_1.bias");
-    const HostT &w2 = T("unet.time_embedding.linear_2.weight"), &b2 = T("unet.time_embedding.linear_2.bias");
-    std::vector<float> e(320), h(1280);
-    const float t = (float)cfg.timestep;
+    if (te_w1.empty()) {
+      te_w1 = T("unet.time_embedding.linear_1.weight").d; te_b1 = T("unet.time_embedding.linear_1.bias").d;
+      te_w2 = T("unet.time_embedding.linear_2.weight").d; te_b2 = T("unet.time_embedding.linear_2.bias").d;
+    }
+    temb = temb_for(cfg.timestep);
+    cur_timestep = cfg.timestep;
+  }
+  std::vector<float> temb_for(int timestep) const {
+    struct V { const std::vector<float>& d; };
+    const V w1{te_w1}, b1{te_b1}, w2{te_w2}, b2{te_b2};
+    std::vector<float> e(320), h(1280), temb;
+    const float t = (float)timestep;
     for (int i = 0; i < 160; ++i) {   // Timesteps(320, flip_sin_to_cos=True, freq_shift=0), fp32
       const float f = std::exp(-std::log(10000.0f) * (float)i / 160.0f);
       e[i] = std::cos(t * f);
@@ -409,20 +431,23 @@ struct gp_engine {
       for (int i = 0; i < 1280; ++i) s += (double)w2.d[(size_t)o * 1280 + i] * h[i];
       temb[o] = (float)s;
     }
+    return temb;
   }
-  std::vector<float> temb_proj(const std::string& key) {   // time_emb_proj(silu(emb)), SURVEY.md F8
-    const HostT &w = T(key + ".weight"), &b = T(key + ".bias");
-    const int cout = (int)w.shape[0];
+  static std::vector<float> temb_proj_of(const std::vector<float>& w, const std::vector<float>& b, const std::vector<float>& emb) {
+    const int cout = (int)b.size();
+    std::vector<double> se(1280);
+    for (int i = 0; i < 1280; ++i) se[i] = emb[i] / (1.0 + std::exp(-(double)emb[i]));
     std::vector<float> out(cout);
     for (int o = 0; o < cout; ++o) {
-      double s = b.d[o];
-      for (int i = 0; i < 1280; ++i) {
-        const double x = temb[i];
-        s += (double)w.d[(size_t)o * 1280 + i] * (x / (1.0 + std::exp(-x)));
-      }
+      double s = b[o];
+      const float* wr = &w[(size_t)o * 1280];
+      for (int i = 0; i < 1280; ++i) s += (double)wr[i] * se[i];
       out[o] = (float)s;
     }
     return out;
+  }
+  std::vector<float> temb_proj(const std::string& key) {   // time_emb_proj(silu(emb)), SURVEY.md F8
+    return temb_proj_of(T(key + ".weight").d, T(key + ".bias").d, temb);
   }
 
   // ------------------------------------------------------------------ graph pieces
@@ -453,11 +478,22 @@ struct gp_engine {
     T4 h = b.alloc(x0.N, x0.H, x0.W, cout);
     {
       std::vector<float> tp;
-      if (temb_on && !packed.count(p + ".conv1")) tp = temb_proj(p + ".time_emb_proj");
+      const bool first = temb_on && !packed.count(p + ".conv1");
+      if (first) tp = temb_proj(p + ".time_emb_proj");
       ConvArgs c;
       c.srcs = xs;
       c.gn = &norm_w(p + ".norm1"); c.gn_name = p + ".norm1"; c.gn_eps = eps;
       c.w = &conv_w(p + ".conv1", {cin}, "", {}, tp.empty() ? nullptr : &tp);
+      if (first) {   // what gp_set_timestep needs to re-fold this bias for another timestep
+        TembLayer tl;
+        tl.key = p;
+        tl.w = T(p + ".time_emb_proj.weight").d;
+        tl.b = T(p + ".time_emb_proj.bias").d;
+        tl.conv_bias = T(p + ".conv1.bias").d;
+        tl.dev_bias = c.w->bias;
+        tl.cout = cout;
+        temb_layers.push_back(std::move(tl));
+      }
       c.out = h;
       c.want_stats = true;     // feeds norm2
       b.conv(p + ".conv1", c);
@@ -758,6 +794,12 @@ struct gp_engine {
     }
     // conv_out, DDIM(beta=1) x0 = -v, /0.18215, post_quant_conv  ->  one 3x3 conv 320->4 (App. C.3)
     if (!packed.count("unet.tail")) {
+      if (pq_dev == nullptr) {       // decode_pred of a caller-supplied latent applies post_quant_conv itself (gp_decode)
+        std::vector<float> pqm = T("vae.post_quant_conv.weight").d;
+        const std::vector<float>& pqb = T("vae.post_quant_conv.bias").d;
+        pqm.insert(pqm.end(), pqb.begin(), pqb.end());
+        pq_dev = upload(pqm);
+      }
       const HostT &w = T(u + ".conv_out.weight"), &bb = T(u + ".conv_out.bias"), &pq = T("vae.post_quant_conv.weight"), &pb = T("vae.post_quant_conv.bias");
       folded["unet.tail"].assign((size_t)8 * 320 * 9, 0.f);
       std::vector<float>& f = folded["unet.tail"];
@@ -847,7 +889,7 @@ struct gp_engine {
     b.release(c1);
     return out;
   }
-  void dpt_head(Builder& b, T4 feats[4], float* out_f32, unsigned int* mm_scratch) {
+  void dpt_head(Builder& b, T4 feats[4], float* out_f32, unsigned int* mm_scratch, int* out_h, int* out_w) {
     // feats (up-block order): [1280@h/4, 1280@h/2, 640@h, 320@h]; reference reverses (:479)
     T4 f0 = feats[3], f1 = feats[2], f2 = feats[1], f3 = feats[0];
     T4 f0u = b.alloc(f0.N, 2 * f0.H, 2 * f0.W, 320);
@@ -869,8 +911,23 @@ struct gp_engine {
       if (li == 0) {
         y = dpt_rcu(b, lp + ".residual_layer2", f, nullptr);
       } else {
-        GP_REQUIRE(x.H == f.H && x.W == f.W, "DPT fusion: feature sizes must match (input multiple of 64)");
-        T4 s = dpt_rcu(b, lp + ".residual_layer1", f, &x);   // x + (f + conv2(...))
+        // dpt_head.py:297-300: a skip feature whose extent differs from the running map's (odd pyramid levels) is
+        // resized to it, bilinear, align_corners=False
+        T4 fr = f;
+        const bool rs = x.H != f.H || x.W != f.W;
+        if (rs) {
+          fr = b.alloc(x.N, x.H, x.W, 256);
+          if (!b.measuring()) {
+            const void* src = b.ptr(f);
+            void* dst = b.ptr(fr);
+            const int n = f.N, h = f.H, w = f.W, oh = x.H, ow = x.W;
+            const bool bf = bf16, spl = split;
+            b.custom(lp + ".resize_skip", 1, (double)f.bytes() + (double)fr.bytes(),
+                     [=](cudaStream_t st) { return bilinear_resize(src, dst, n, h, w, oh, ow, 256, bf, st, spl); });
+          }
+        }
+        T4 s = dpt_rcu(b, lp + ".residual_layer1", fr, &x);   // x + (f + conv2(...))
+        if (rs) b.release(fr);
         b.release(x);
         y = dpt_rcu(b, lp + ".residual_layer2", s, nullptr);
         b.release(s);
@@ -898,8 +955,10 @@ struct gp_engine {
     b.direct("dpt.head.head.4", h2, 32, direct_w("dpt.head.head.4", 32), h2, 0, out_f32, 0);
     const int N = h2.N;
     const long long HW = (long long)h2.H * h2.W;
+    *out_h = h2.H; *out_w = h2.W;
     b.release(h2);
-    b.custom("dpt.minmax", 3, 3.0 * N * HW * 4, [=](cudaStream_t s) { return minmax_normalize(out_f32, N, HW, mm_scratch, s); });
+    float** slot = b.out_slot;
+    b.custom("dpt.minmax", 3, 3.0 * N * HW * 4, [=](cudaStream_t s) { return minmax_normalize(slot ? *slot : out_f32, N, HW, mm_scratch, s); });
   }
 
   std::unordered_map<std::string, std::vector<float>> folded;   // host fp32 folded weights (live until packed)
@@ -908,12 +967,13 @@ struct gp_engine {
     // The VAE needs multiples of 8 (three stride-2 stages); the UNet handles odd latent extents like diffusers
     // (ceil on the way down, resize to the skip's size on the way up).  The DPT head's fusion stages assume
     // matching pyramid sizes: multiples of 64 there (the reference resizes the skip bilinearly otherwise).
-    if (cfg.readout == GP_READOUT_DPT)
-      GP_REQUIRE(H % 64 == 0 && W % 64 == 0, "the DPT readout supports H, W multiples of 64");
-    GP_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of 8 (AutoencoderKL)");
+    // Any H, W >= 32, like the reference: the VAE's stride-2 stages floor (asymmetric padding), so the decoded map is
+    // 8*floor(H/8) x 8*floor(W/8); the DPT fusion stages resize a skip feature to the running map when the pyramid
+    // extents differ (dpt_head.py:297-300), so its map is a multiple of 64 that covers the input.  __call__'s
+    // match_input_res resize brings either back to the input size (genpercept_pipeline.py:301-307).
     // persistent buffers first so their offsets are identical in both passes
     const size_t in_off = b.raw_alloc((size_t)B * 3 * H * W * 4);
-    const size_t out_off = b.raw_alloc((size_t)B * 3 * H * W * 4);
+    const size_t out_off = b.raw_alloc((size_t)B * 3 * (H + 64) * (W + 64) * 4);
     const size_t sums_off = b.raw_alloc((size_t)B * 2560 * 2 * 4);
     const size_t ss_off = b.raw_alloc((size_t)B * 2560 * 2 * 4);
     const size_t mm_off = b.raw_alloc((size_t)B * 2 * 4);
@@ -922,7 +982,9 @@ struct gp_engine {
     if (!b.measuring()) {
       plan->in_staging = b.raw_ptr(in_off);
       plan->out_f32 = reinterpret_cast<float*>(b.raw_ptr(out_off));
+      plan->out_dst = plan->out_f32;
       out_f32 = plan->out_f32;
+      b.out_slot = &plan->out_dst;
       b.gn_sums = reinterpret_cast<float*>(b.raw_ptr(sums_off));
       b.gn_ss = reinterpret_cast<float*>(b.raw_ptr(ss_off));
     }
@@ -933,12 +995,15 @@ struct gp_engine {
     b.stage = GP_STAGE_UNET;
     const bool dpt = cfg.readout == GP_READOUT_DPT;
     T4 feats[4];
-    T4 z = b.alloc(B, H / 8, W / 8, 8);
+    T4 z = b.alloc(B, latent.H, latent.W, 8);
     unet(b, latent, dpt, &z, feats);
     b.stage = GP_STAGE_READOUT;
-    if (dpt) dpt_head(b, feats, out_f32, mm);
+    int oh = 8 * latent.H, ow = 8 * latent.W;
+    if (dpt) dpt_head(b, feats, out_f32, mm, &oh, &ow);
     else vae_decoder(b, z, out_f32);
+    GP_REQUIRE(oh <= H + 64 && ow <= W + 64, "result extent exceeds the plan's output buffer");
     if (!b.measuring()) {
+      plan->outH = oh; plan->outW = ow;
       plan->kept["rgb"] = Kept{rgb8, nullptr, 3};
       plan->kept["rgb_latent"] = Kept{latent, nullptr, 4};
       if (!dpt) plan->kept["z"] = Kept{z, nullptr, 4};
@@ -1056,11 +1121,24 @@ gp_status gp_finalize(gp_engine* e) {
 gp_status gp_plan(gp_engine* e, int B, int H, int W) {
   return guarded(e, [&]() {
     if (!e->finalized) throw GpError(GP_ERR_STATE, "gp_plan before gp_finalize");
-    GP_REQUIRE(B >= 1 && H >= 64 && W >= 64, "gp_plan: bad shape");
+    GP_REQUIRE(B >= 1 && H >= 32 && W >= 32, "gp_plan: bad shape (H, W >= 32)");
     GP_CUDA(cudaSetDevice(e->cfg.device));
     auto key = std::make_tuple(B, H, W);
     auto it = e->plans.find(key);
-    if (it != e->plans.end()) { e->cur = it->second.get(); return; }
+    if (it != e->plans.end()) { e->cur = it->second.get(); e->cur->last_used = ++e->use_clock; return; }
+    // Bounded plan cache (a folder of in-the-wild images yields a new (H, W) per aspect ratio): evict the least
+    // recently used plans — graph execs destroyed, arena freed — before building another one.
+    static const size_t max_plans = std::getenv("GP_MAX_PLANS") ? (size_t)std::max(1, std::atoi(std::getenv("GP_MAX_PLANS"))) : 4;
+    while (e->plans.size() >= max_plans) {
+      auto victim = e->plans.begin();
+      for (auto jt = e->plans.begin(); jt != e->plans.end(); ++jt)
+        if (jt->second->last_used < victim->second->last_used) victim = jt;
+      GP_CUDA(cudaDeviceSynchronize());
+      for (auto& g : victim->second->graphs) cudaGraphExecDestroy(g.second);
+      if (victim->second->arena) cudaFree(victim->second->arena);
+      if (e->cur == victim->second.get()) e->cur = nullptr;
+      e->plans.erase(victim);
+    }
     Builder m(e->bf16, true, nullptr, e->split);
     e->build(m, nullptr, B, H, W);
     std::unique_ptr<Plan> p(new Plan());
@@ -1077,8 +1155,36 @@ gp_status gp_plan(gp_engine* e, int B, int H, int W) {
       p->launches += op.launches;
       p->igemm_flops += op.flops;
     }
+    p->last_used = ++e->use_clock;
     e->cur = p.get();
     e->plans[key] = std::move(p);
+  });
+}
+
+int gp_plan_count(gp_engine* e) { return e ? (int)e->plans.size() : 0; }
+
+gp_status gp_set_timestep(gp_engine* e, int timestep) {
+  return guarded(e, [&]() {
+    if (!e->finalized) throw GpError(GP_ERR_STATE, "gp_set_timestep before gp_finalize");
+    GP_REQUIRE(timestep >= 1 && timestep <= 1000, "gp_set_timestep: timestep must be in [1, 1000]");
+    if (timestep == e->cur_timestep) return;
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    auto it = e->temb_cache.find(timestep);
+    if (it == e->temb_cache.end()) {
+      const std::vector<float> emb = e->temb_for(timestep);
+      std::vector<std::vector<float>> biases(e->temb_layers.size());
+      parallel_for((int)e->temb_layers.size(), [&](int i) {
+        const auto& tl = e->temb_layers[(size_t)i];
+        std::vector<float> b = gp_engine::temb_proj_of(tl.w, tl.b, emb);
+        for (int o = 0; o < tl.cout; ++o) b[(size_t)o] += tl.conv_bias[(size_t)o];
+        biases[(size_t)i] = std::move(b);
+      });
+      it = e->temb_cache.emplace(timestep, std::move(biases)).first;
+    }
+    GP_CUDA(cudaDeviceSynchronize());          // nothing in flight may still read the old biases
+    for (size_t i = 0; i < e->temb_layers.size(); ++i)
+      GP_CUDA(cudaMemcpy(e->temb_layers[i].dev_bias, it->second[i].data(), (size_t)e->temb_layers[i].cout * 4, cudaMemcpyHostToDevice));
+    e->cur_timestep = timestep;
   });
 }
 
@@ -1091,20 +1197,31 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
     if (dpt) out_channels = 1;
     GP_REQUIRE(rgb && out && (out_channels == 1 || out_channels == 3), "gp_infer: bad arguments");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    p->last_used = ++e->use_clock;
     const size_t npix = (size_t)p->B * p->H * p->W;
+    const size_t npix_out = (size_t)p->B * p->outH * p->outW;
     int kind = 0;
     size_t esz = 1;
     if (rgb_dtype == GP_U8) { kind = 0; esz = 1; }
     else if (rgb_dtype == GP_F16) { kind = 1; esz = 2; }
     else if (rgb_dtype == GP_F32) { kind = 2; esz = 4; }
     else throw GpError(GP_ERR_INVALID, "gp_infer: rgb dtype must be u8, f16 or f32");
-    GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, npix * 3 * esz, rgb_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    GP_CUDA(preprocess_rgb(p->in_staging, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
+    // a device input is read where it lies; only host inputs go through the plan's staging buffer
+    const void* src = rgb;
+    if (rgb_on_host) {
+      GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, npix * 3 * esz, cudaMemcpyHostToDevice, s));
+      src = p->in_staging;
+    }
+    GP_CUDA(preprocess_rgb(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
     // 2 = auto: replay a graph where the launch stream is the bottleneck — small plans (measured: +15 % at 384x384,
     // +8 % at 768x768 with one image, nothing at batch 8)
     const bool use_graph = e->cfg.use_cuda_graph == 1 ||
                            (e->cfg.use_cuda_graph == 2 && (long long)p->B * p->H * p->W <= 2LL * 768 * 768);
-    if (use_graph && p->eager_runs > 0) {
+    // eager launches write the result straight into a device `out`; a captured graph has the plan's own buffer baked in
+    const bool graph_now = use_graph && p->eager_runs > 0;
+    p->out_dst = (graph_now || out_on_host) ? p->out_f32 : out;
+    if (graph_now) {
       auto it = p->graphs.find(out_channels);
       if (it == p->graphs.end()) {
         cudaStream_t cs;
@@ -1126,8 +1243,54 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
       GP_CUDA(run_ops(p, GP_STAGE_VAE_ENCODE, GP_STAGE_READOUT, out_channels, s));
       p->eager_runs++;
     }
-    GP_CUDA(cudaMemcpyAsync(out, p->out_f32, npix * out_channels * 4, out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    if (p->out_dst != out)
+      GP_CUDA(cudaMemcpyAsync(out, p->out_f32, npix_out * out_channels * 4, out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    p->out_dst = p->out_f32;
     if (rgb_on_host || out_on_host) GP_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+gp_status gp_encode(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, float* latent_dev, void* stream) {
+  return guarded(e, [&]() {
+    Plan* p = e->cur;
+    if (!p) throw GpError(GP_ERR_NO_PLAN, "gp_encode: no plan (call gp_plan)");
+    GP_REQUIRE(rgb && latent_dev, "gp_encode: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    int kind = 0;
+    size_t esz = 1;
+    if (rgb_dtype == GP_U8) { kind = 0; esz = 1; }
+    else if (rgb_dtype == GP_F16) { kind = 1; esz = 2; }
+    else if (rgb_dtype == GP_F32) { kind = 2; esz = 4; }
+    else throw GpError(GP_ERR_INVALID, "gp_encode: rgb dtype must be u8, f16 or f32");
+    const void* src = rgb;
+    if (rgb_on_host) {
+      GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, (size_t)p->B * p->H * p->W * 3 * esz, cudaMemcpyHostToDevice, s));
+      src = p->in_staging;
+    }
+    GP_CUDA(preprocess_rgb(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
+    GP_CUDA(run_ops(p, GP_STAGE_VAE_ENCODE, GP_STAGE_VAE_ENCODE, 1, s));
+    const T4& l = p->kept["rgb_latent"].t;
+    GP_CUDA(nhwc8_to_nchw_f32(p->arena + l.off, latent_dev, l.N, l.H, l.W, 4, e->bf16, s, e->split));
+    if (rgb_on_host) GP_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+gp_status gp_decode(gp_engine* e, const float* latent_dev, int apply_post_quant, float* out_dev, int out_channels, void* stream) {
+  return guarded(e, [&]() {
+    Plan* p = e->cur;
+    if (!p) throw GpError(GP_ERR_NO_PLAN, "gp_decode: no plan (call gp_plan)");
+    if (e->cfg.readout == GP_READOUT_DPT) throw GpError(GP_ERR_STATE, "gp_decode: the DPT readout has no latent decoder");
+    GP_REQUIRE(latent_dev && out_dev && (out_channels == 1 || out_channels == 3), "gp_decode: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    const T4& z = p->kept["z"].t;
+    GP_CUDA(nchw4_affine_to_nhwc8(latent_dev, p->arena + z.off, z.N, z.H, z.W, 1.0f / kLatentScale,
+                                  apply_post_quant ? e->pq_dev : nullptr, apply_post_quant ? e->pq_dev + 16 : nullptr, e->bf16, s,
+                                  e->split));
+    p->out_dst = out_dev;
+    GP_CUDA(run_ops(p, GP_STAGE_READOUT, GP_STAGE_READOUT, out_channels, s));
+    p->out_dst = p->out_f32;
   });
 }
 
@@ -1136,6 +1299,8 @@ gp_status gp_run_stage(gp_engine* e, int stage, int out_channels, void* stream) 
     Plan* p = e->cur;
     if (!p) throw GpError(GP_ERR_NO_PLAN, "gp_run_stage: no plan");
     if (e->cfg.readout == GP_READOUT_DPT) out_channels = 1;
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    p->out_dst = p->out_f32;
     GP_CUDA(run_ops(p, stage, stage, out_channels, reinterpret_cast<cudaStream_t>(stream)));
   });
 }
@@ -1144,7 +1309,7 @@ gp_status gp_tensor_shape(gp_engine* e, const char* name, int64_t shape[4]) {
   return guarded(e, [&]() {
     Plan* p = e->cur;
     if (!p) throw GpError(GP_ERR_NO_PLAN, "no plan");
-    if (std::string(name) == "out") { shape[0] = p->B; shape[1] = 3; shape[2] = p->H; shape[3] = p->W; return; }
+    if (std::string(name) == "out") { shape[0] = p->B; shape[1] = 3; shape[2] = p->outH; shape[3] = p->outW; return; }
     auto it = p->kept.find(name);
     GP_REQUIRE(it != p->kept.end(), std::string("unknown tensor ") + name);
     shape[0] = it->second.t.N; shape[1] = it->second.creal; shape[2] = it->second.t.H; shape[3] = it->second.t.W;
@@ -1157,7 +1322,7 @@ gp_status gp_read_tensor(gp_engine* e, const char* name, float* host_out, size_t
     if (!p) throw GpError(GP_ERR_NO_PLAN, "no plan");
     GP_CUDA(cudaDeviceSynchronize());
     if (std::string(name) == "out") {
-      const size_t n = (size_t)p->B * 3 * p->H * p->W;
+      const size_t n = (size_t)p->B * 3 * p->outH * p->outW;
       GP_REQUIRE(cap >= n, "gp_read_tensor: buffer too small");
       GP_CUDA(cudaMemcpy(host_out, p->out_f32, n * 4, cudaMemcpyDeviceToHost));
       return;
@@ -1227,6 +1392,7 @@ gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream) {
     cudaEvent_t a, b;
     GP_CUDA(cudaEventCreate(&a));
     GP_CUDA(cudaEventCreate(&b));
+    p->out_dst = p->out_f32;
     for (auto& op : p->ops) {
       op.usec = 0;
       if (op.variant != 0 && op.variant != out_channels) continue;

@@ -153,6 +153,9 @@ class Builder {
   size_t arena_bytes() const { return arena_.high_water(); }
   float* gn_sums = nullptr;   // [N][Cmax][2]
   float* gn_ss = nullptr;
+  // When set, ops that write the final fp32 map (ConvArgs::out_f32 / direct(..., out_f32)) read their destination from
+  // *out_slot at LAUNCH time, so gp_infer can point them at the caller's device buffer (no copy of the result).
+  float** out_slot = nullptr;
 
  private:
   void push(const std::string& name, int launches, double flops, double bytes,

@@ -369,9 +369,13 @@ void fattn_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 long long* fattn_get_trace() { return g_trace; }
 
 cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};
   static bool poly = false;
   static int stagger = 0, pingpong = 1, pp_early = 1;   // r1l trace: period 3560 (4) / 3350 (3) / 3290 (2) / 3180 (1) / 3440 (0)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  bool& attr_set = attr_dev[dev];      // function attributes are per device
   if (!attr_set) {
     const void* fns[4] = {(const void*)fattn_kernel<false, false>, (const void*)fattn_kernel<false, true>,
                           (const void*)fattn_kernel<true, false>, (const void*)fattn_kernel<true, true>};

@@ -280,7 +280,7 @@ const char* igemm_finalize(IgemmParams* p) {
         p->nkb[0] != 9 * p->kc_count + p->kc_sc || p->npass != 1 || p->gridW % 128 || p->gridH % p->TH)
       return "patch mode needs TW = 128, TH = MT, full tiles and a single-source 3x3 tap table (+ shortcut chunks)";
     if (p->gn_ss && p->gn_C != p->kc_count * 64) return "patch mode: GroupNorm channels must equal the source's";
-    p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
+    p->a_slot_bytes = 136 * (p->TH + 2) * 128;      // igemm_patch.cu kPP: 130 pixels per patch row at a 136-row pitch
     st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0) - 2 * p->a_slot_bytes) / (p->BN * 128);
     if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
       const int v = atoi(env);

@@ -34,6 +34,7 @@ namespace {
 
 constexpr int kPatchThreads = 384;
 constexpr int kPW = kBM + 2;      // patch width in pixels (TW = 128)
+constexpr int kPP = 136;          // patch row pitch in pixels: every image row of the patch starts on a 1024-byte swizzle atom
 
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -46,6 +47,18 @@ __device__ __forceinline__ float silu_tanh(float x) {   // x * sigmoid(x) = h + 
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// Two channels per special-function op: the transform of a 64-channel patch is bound by the MUFU (16 results / clk / SM
+// with tanh.approx.f32: 520 x 64 / 16 = 2080 cycles per K chunk, against 4608 cycles of MMA per chunk and a TMA load
+// that cannot start before the previous use of the slot retires).  tanh.approx.f16x2 has the same ~2^-11 relative
+// error as the f32 form; h and the final h + h * tanh(h) stay in fp32.
+__device__ __forceinline__ uint32_t silu_pair_f16(float ha, float hb) {     // inputs are already x / 2
+  const __half2 h2 = __floats2half2_rn(ha, hb);
+  uint32_t hi = *reinterpret_cast<const uint32_t*>(&h2), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(hi));
+  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&ti));
+  const __half2 y = __floats2half2_rn(fmaf(ha, t.x, ha), fmaf(hb, t.y, hb));
+  return *reinterpret_cast<const uint32_t*>(&y);
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
@@ -55,8 +68,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
   const int stages = p.stages;                       // depth of the weight ring
   uint8_t* sB = smem + 2 * p.a_slot_bytes;
   uint8_t* stg_base = sB + stages * b_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));
-  uint64_t* a_ready = a_full + 2;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));   // [slot][patch row]
+  uint64_t* a_ready = a_full + 8;
   uint64_t* a_empty = a_ready + 2;
   uint64_t* b_full = a_empty + 2;
   uint64_t* b_empty = b_full + stages;
@@ -68,16 +81,15 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
-  const int prows = (p.TH + 2) * kPW;                // pixels (= 128-byte rows) of a patch
-  const uint32_t patch_bytes = (uint32_t)prows * 128;
+  const int prows = (p.TH + 2) * kPP;                // 128-byte rows of a patch slot (130 pixels + 6 unused per image row)
   const int kc_all = p.kc_count + p.kc_sc;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmPatch);
     tma_prefetch_desc(&p.tmPatch2);
     tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < 8; ++i) mbar_init(&a_full[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1);
       mbar_init(&a_ready[i], 128);                   // the transform warpgroup
       mbar_init(&a_empty[i], p.MT);                  // one tcgen05.commit per MMA issuer
     }
@@ -111,9 +123,13 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
           const bool main = kc < p.kc_count;
           mbar_wait(&a_empty[slot], phase ^ 1, 1);
           if (leader) {
-            mbar_expect_tx(&a_full[slot], patch_bytes);
-            tma_load_4d(smem + slot * p.a_slot_bytes, main ? &p.tmPatch : &p.tmPatch2, &a_full[slot],
-                        (main ? kc : kc - p.kc_count) * kBK, x0, y0, t.z1);
+            // one box per image row of the patch, each on its own barrier: the transform starts on the first row while
+            // the others are still in flight
+            for (int g = 0; g < p.TH + 2; ++g) {
+              mbar_expect_tx(&a_full[slot * 4 + g], (uint32_t)(kPW * 128));
+              tma_load_4d(smem + slot * p.a_slot_bytes + g * (kPP * 128), main ? &p.tmPatch : &p.tmPatch2, &a_full[slot * 4 + g],
+                          (main ? kc : kc - p.kc_count) * kBK, x0, y0 + g, t.z1);
+            }
           }
           __syncwarp();
           if (++slot == 2) { slot = 0; phase ^= 1; }
@@ -154,8 +170,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
       uint32_t acc_phase = 0;
       int tap_off[9];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((p.seg[0][tap].dy + 1 + h) * kPW + p.seg[0][tap].dx + 1) * 128;
-      const int centre_off = ((1 + h) * kPW + 1) * 128;
+      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((p.seg[0][tap].dy + 1 + h) * kPP + p.seg[0][tap].dx + 1) * 128;
+      const int centre_off = ((1 + h) * kPP + 1) * 128;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
@@ -209,10 +225,12 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
     const int tt = threadIdx.x - 256;                // 0..127
     const int cpos = tt & 7;                         // 16-byte position inside the 128-byte row
     const int rbase = tt >> 3;                       // rows rbase, rbase + 16, ...
-    // SWIZZLE_128B: position = logical 16-byte chunk ^ (row & 7); rows advance by 16, so (row & 7) is fixed per thread
+    // SWIZZLE_128B: position = logical 16-byte chunk ^ (row & 7); rows advance by 16 and the pitch (136) is a multiple
+    // of 8, so (row & 7) is fixed per thread
     const int jlog = cpos ^ (rbase & 7);             // this thread's logical channel group (8 channels) in every chunk
     const bool do_gn = p.gn_ss != nullptr;
     const bool do_silu = p.gn_silu != 0;
+    const bool tanh32 = p.gn_silu == 2;              // A/B switch: tanh.approx.f32 instead of the f16x2 form
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -224,34 +242,55 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
         float sc[8], sh[8];
         if (xf) {                                    // fetched before the patch lands
           const float4* sp = reinterpret_cast<const float4*>(ssn + (kc * kBK + jlog * 8) * 2);
+          const float pre = (do_silu && !BF16 && !tanh32) ? 0.5f : 1.f;   // the fp16 SiLU form takes h = x / 2: folded into the affine
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float4 a = __ldg(sp + e);
-            sc[2 * e] = a.x; sh[2 * e] = a.y; sc[2 * e + 1] = a.z; sh[2 * e + 1] = a.w;
+            sc[2 * e] = a.x * pre; sh[2 * e] = a.y * pre; sc[2 * e + 1] = a.z * pre; sh[2 * e + 1] = a.w * pre;
           }
         }
-        mbar_wait(&a_full[slot], phase, 8);
-        if (xf) {
+        int landed = 0;                              // patch rows whose barrier this thread has passed
+        if (!xf) {
+          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+        } else {
           const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
           int py = 0, px = rbase;                    // rbase < 16 < kPW
-          for (int r = rbase; r < prows; r += 16) {
-            const bool inside = (unsigned)(y0 + py) < (unsigned)p.gridH && (unsigned)(x0 + px) < (unsigned)p.gridW;
-            if (inside) {
-              const uint32_t addr = base + r * 128;
-              uint32_t w[4];
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+          for (int r = rbase; r < prows; r += 64) {  // four rows in flight per thread
+            uint32_t w[4][4];
+            bool ok[4];
+            {
+              const int last = min(r + 48, prows - 1) / kPP;      // deepest patch row this group of four touches
+              for (; landed <= last; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = r + 16 * u;
+              ok[u] = rr < prows && px < kPW && (unsigned)(y0 + py) < (unsigned)p.gridH && (unsigned)(x0 + px) < (unsigned)p.gridW;
+              if (ok[u])
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "r"(base + rr * 128));
+              px += 16;
+              if (px >= kPP) { px -= kPP; ++py; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (!ok[u]) continue;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a = fmaf(cvt16<BF16>((uint16_t)(w[e] & 0xFFFF)), sc[2 * e], sh[2 * e]);
-                float b = fmaf(cvt16<BF16>((uint16_t)(w[e] >> 16)), sc[2 * e + 1], sh[2 * e + 1]);
-                if (do_silu) { a = silu_tanh(a); b = silu_tanh(b); }
-                w[e] = pack16<BF16>(a, b);
+                float a = fmaf(cvt16<BF16>((uint16_t)(w[u][e] & 0xFFFF)), sc[2 * e], sh[2 * e]);
+                float b = fmaf(cvt16<BF16>((uint16_t)(w[u][e] >> 16)), sc[2 * e + 1], sh[2 * e + 1]);
+                if (BF16 || tanh32) {
+                  if (do_silu) { a = silu_tanh(a); b = silu_tanh(b); }
+                  w[u][e] = pack16<BF16>(a, b);
+                } else {
+                  w[u][e] = do_silu ? silu_pair_f16(a, b) : pack16<BF16>(a, b);
+                }
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (r + 16 * u) * 128), "r"(w[u][0]),
+                           "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
             }
-            px += 16;
-            if (px >= kPW) { px -= kPW; ++py; }
           }
+          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);   // keep the phases in step
           fence_proxy_async_shared();                // generic-proxy writes -> visible to the tensor core's reads
         }
         mbar_arrive(&a_ready[slot]);

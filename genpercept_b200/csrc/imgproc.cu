@@ -88,6 +88,11 @@ const AxisTable& axis_table(int dev, int in_size, int out_size, int mode) {
   auto key = std::make_tuple(dev, in_size, out_size, mode);
   auto it = g_tables.find(key);
   if (it != g_tables.end()) return it->second;
+  if (g_tables.size() >= 64) {   // every distinct (in, out) extent is a table: bound the cache (a folder of in-the-wild images)
+    ck(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    for (auto& kv : g_tables) { cudaFree(kv.second.xmin); cudaFree(kv.second.xsize); cudaFree(kv.second.w); }
+    g_tables.clear();
+  }
   std::vector<int> xmin, xsize;
   std::vector<float> w;
   AxisTable t;

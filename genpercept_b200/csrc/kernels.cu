@@ -786,6 +786,62 @@ cudaError_t preprocess_rgb(const void* in, int in_kind, void* out, int N, int H,
   return cudaGetLastError();
 }
 
+namespace {
+// 16-bit NHWC8 (first `c` channels) -> fp32 NCHW [N, c, H, W]
+template <bool BF16>
+__global__ void nhwc8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int N, long long HW, int c, int lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  const int n = (int)(i / HW);
+  const long long p = i % HW;
+  float f[8];
+  load8<BF16>(in + i * (lo ? 16 : 8), lo, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < c) out[((long long)n * c + k) * HW + p] = f[k];
+}
+// fp32 NCHW [N, 4, H, W] -> y = M (x * pre) + b per pixel -> 16-bit NHWC8 (channels 4..7 zero).  m: [4][4] row-major
+// (null = identity), b: [4] (null = 0).
+template <bool BF16>
+__global__ void nchw4_affine_to_nhwc8_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, long long HW,
+                                             float pre, const float* __restrict__ m, const float* __restrict__ b, int lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  const int n = (int)(i / HW);
+  const long long p = i % HW;
+  float x[4], f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = in[((long long)n * 4 + k) * HW + p] * pre;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    if (m) {
+      float a = b ? b[o] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a = fmaf(m[o * 4 + k], x[k], a);
+      f[o] = a;
+    } else {
+      f[o] = x[o];
+    }
+  }
+  store8<BF16>(out + i * (lo ? 16 : 8), lo, f);
+}
+}  // namespace
+
+cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, int c, bool bf16, cudaStream_t s, bool split) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  GP_DISPATCH_BF16(bf16, (nhwc8_to_nchw_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), out, N, HW, c, split ? 8 : 0)));
+  return cudaGetLastError();
+}
+
+cudaError_t nchw4_affine_to_nhwc8(const float* in, void* out, int N, int H, int W, float pre, const float* m, const float* b,
+                                  bool bf16, cudaStream_t s, bool split) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  GP_DISPATCH_BF16(bf16, (nchw4_affine_to_nhwc8_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                             in, reinterpret_cast<uint16_t*>(out), N, HW, pre, m, b, split ? 8 : 0)));
+  return cudaGetLastError();
+}
+
 cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s) {
   minmax_init_kernel<<<(N + 63) / 64, 64, 0, s>>>(scratch, N);
   int bx = (int)((HW + 256 * 8 - 1) / (256 * 8));
@@ -833,6 +889,48 @@ cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, b
   const long long total = rows * groups;
   GP_DISPATCH_BF16(bf16, (softmax_groups_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
                              reinterpret_cast<uint16_t*>(x), rows, ld, groups, n, split ? ld : 0)));
+  return cudaGetLastError();
+}
+
+namespace {
+// F.interpolate(size=(OH,OW), mode="bilinear", align_corners=False): src = max((dst + 0.5) * in/out - 0.5, 0)
+template <bool BF16>
+__global__ void bilinear_resize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W, int OH,
+                                       int OW, int C, float sy, float sx, long long total_vec, int lo) {
+  const int nvec = C / 8;
+  const int xs = lo ? 2 * C : C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long r = i / nvec;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float h1 = fy - y0, w1 = fx - x0, h0 = 1.f - h1, w0 = 1.f - w1;
+    const uint16_t* b = in + ((long long)n * H * W) * xs + v * 8;
+    float a00[8], a01[8], a10[8], a11[8], o[8];
+    load8<BF16>(b + ((long long)y0 * W + x0) * xs, lo, a00);
+    load8<BF16>(b + ((long long)y0 * W + x1) * xs, lo, a01);
+    load8<BF16>(b + ((long long)y1 * W + x0) * xs, lo, a10);
+    load8<BF16>(b + ((long long)y1 * W + x1) * xs, lo, a11);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = h0 * (w0 * a00[e] + w1 * a01[e]) + h1 * (w0 * a10[e] + w1 * a11[e]);
+    store8<BF16>(out + (((long long)n * OH + oy) * OW + ox) * xs + v * 8, lo, o);
+  }
+}
+}  // namespace
+
+cudaError_t bilinear_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, bool bf16, cudaStream_t s,
+                            bool split) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const long long total_vec = (long long)N * OH * OW * (C / 8);
+  GP_DISPATCH_BF16(bf16, (bilinear_resize_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, OH, OW, C,
+                             (float)H / (float)OH, (float)W / (float)OW, total_vec, split ? C : 0)));
   return cudaGetLastError();
 }
 

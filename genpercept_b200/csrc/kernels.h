@@ -63,9 +63,18 @@ cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, b
 // F.interpolate(size=(OH,OW), mode="nearest") on 16-bit NHWC: src = min(floor(dst * in/out), in-1)  (the UNet's
 // Upsample2D with an explicit output size, when H/8 or W/8 is not a multiple of 8)
 cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s);
+// F.interpolate(size=(OH,OW), mode="bilinear", align_corners=False) on 16-bit NHWC (the DPT fusion stage's resize of a
+// skip feature to the running map's size, /root/reference/genpercept/models/dpt_head.py:297-300)
+cudaError_t bilinear_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, bool bf16, cudaStream_t s,
+                            bool split = false);
 // u8 / f16 / f32 NCHW [N,3,H,W] -> 16-bit NHWC8 (channels 3..7 zero); u8 is mapped x/255*2-1.
 cudaError_t preprocess_rgb(const void* in, int in_kind /*0 u8, 1 f16, 2 f32*/, void* out, int N, int H,
                            int W, bool bf16, cudaStream_t s, bool split = false);
+// latent I/O of encode_rgb / decode_pred: 16-bit NHWC8 <-> fp32 NCHW [N,4,H,W]; the second form applies
+// y = M (x * pre) + b per pixel (post_quant_conv(latent / 0.18215), genpercept_pipeline.py:519-521)
+cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, int c, bool bf16, cudaStream_t s, bool split = false);
+cudaError_t nchw4_affine_to_nhwc8(const float* in, void* out, int N, int H, int W, float pre, const float* m /*[4][4] or null*/,
+                                  const float* b /*[4] or null*/, bool bf16, cudaStream_t s, bool split = false);
 // per-image (x - min) / (max - min) over HW fp32 values, in place; scratch: 2 uint32 per image.
 cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s);
 

@@ -49,6 +49,10 @@ def lib():
     L.gp_plan.argtypes = [c_void_p, c_int, c_int, c_int]
     L.gp_infer.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
     L.gp_run_stage.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    L.gp_encode.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    L.gp_decode.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    L.gp_set_timestep.argtypes = [c_void_p, c_int]
+    L.gp_plan_count.argtypes = [c_void_p]
     L.gp_tensor_shape.argtypes = [c_void_p, c_char_p, POINTER(c_int64)]
     L.gp_read_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
     L.gp_write_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
@@ -83,8 +87,8 @@ def _gp_dtype(t):
     return {torch.float32: GP_F32, torch.float16: GP_F16, torch.bfloat16: GP_BF16, torch.uint8: GP_U8}[t]
 
 
-def _stream_ptr():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _check_free(st, what):
@@ -112,6 +116,7 @@ class Engine:
         if st != 0:
             raise RuntimeError(f"gp_create failed: {_STATUS.get(st, st)} (no sm_100a device?)")
         self.plan_shape = None
+        self.out_hw = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -150,6 +155,39 @@ class Engine:
     def plan(self, batch, height, width):
         self._ck(self.L.gp_plan(self.h, batch, height, width), "gp_plan")
         self.plan_shape = (batch, height, width)
+        self.out_hw = self.tensor_shape("out")[2:]      # == (height, width) for multiples of 8 (VAE) / 64 (DPT)
+
+    def plan_count(self):
+        return int(self.L.gp_plan_count(self.h))
+
+    def set_timestep(self, t):
+        """Per-call ``fix_timesteps`` (genpercept_pipeline.py:405-408): re-folds the ResNet biases (cached per t)."""
+        self._ck(self.L.gp_set_timestep(self.h, int(t)), "gp_set_timestep")
+
+    def _sp(self):
+        return _stream_ptr(self.device)
+
+    def encode(self, rgb):
+        """encode_rgb on the device: [B,3,H,W] uint8 / float -> fp32 latent [B,4,H/8,W/8] (cuda)."""
+        B, _, H, W = rgb.shape
+        if self.plan_shape != (B, H, W):
+            self.plan(B, H, W)
+        rgb = (rgb.float() if rgb.dtype == torch.bfloat16 else rgb).contiguous()
+        lat = torch.empty((B, 4) + self.tensor_shape("rgb_latent")[2:], dtype=torch.float32, device=self.device)
+        self._ck(self.L.gp_encode(self.h, c_void_p(rgb.data_ptr()), _gp_dtype(rgb.dtype), 0 if rgb.is_cuda else 1,
+                                  c_void_p(lat.data_ptr()), self._sp()), "gp_encode")
+        return lat
+
+    def decode(self, latent, out_channels=1, post_quant=True):
+        """decode_pred + clip + shift on the device: fp32 latent [B,4,h,w] -> fp32 [B,C,8h,8w] in [0,1] (cuda)."""
+        B, _, h, w = latent.shape
+        if self.plan_shape is None or self.plan_shape[0] != B or tuple(self.tensor_shape("z")[2:]) != (h, w):
+            self.plan(B, 8 * h, 8 * w)
+        latent = latent.to(self.device, torch.float32).contiguous()
+        out = torch.empty((B, out_channels, 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+        self._ck(self.L.gp_decode(self.h, c_void_p(latent.data_ptr()), 1 if post_quant else 0, c_void_p(out.data_ptr()),
+                                  out_channels, self._sp()), "gp_decode")
+        return out
 
     def infer(self, rgb, out_channels=1, out=None):
         """rgb: [B,3,H,W] uint8 (0..255) or float16/float32 in [-1,1]; cuda or cpu tensor.
@@ -162,15 +200,17 @@ class Engine:
             rgb = rgb.float()
         rgb = rgb.contiguous()
         C = 1 if self.readout == "dpt" else out_channels
+        Ho, Wo = self.out_hw
         if out is None:
-            out = torch.empty((B, C, H, W), dtype=torch.float32, device=self.device)
-        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, C, H, W)
+            out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=self.device)
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, C, Ho, Wo), \
+            f"out must be contiguous fp32 {(B, C, Ho, Wo)}"
         self._ck(self.L.gp_infer(self.h, c_void_p(rgb.data_ptr()), _gp_dtype(rgb.dtype), 0 if rgb.is_cuda else 1,
-                                 c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, C, _stream_ptr()), "gp_infer")
+                                 c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, C, self._sp()), "gp_infer")
         return out
 
     def run_stage(self, stage, out_channels=1):
-        self._ck(self.L.gp_run_stage(self.h, stage, out_channels, _stream_ptr()), "gp_run_stage")
+        self._ck(self.L.gp_run_stage(self.h, stage, out_channels, self._sp()), "gp_run_stage")
 
     def tensor_shape(self, name):
         s = (c_int64 * 4)()
@@ -194,7 +234,7 @@ class Engine:
                 "flops": fl.value}
 
     def profile_ops(self, out_channels=1):
-        self._ck(self.L.gp_profile_ops(self.h, out_channels, _stream_ptr()), "gp_profile_ops")
+        self._ck(self.L.gp_profile_ops(self.h, out_channels, self._sp()), "gp_profile_ops")
         res = []
         buf = ctypes.create_string_buffer(256)
         us, fl, by, kd = c_double(), c_double(), c_double(), c_int()

@@ -31,7 +31,7 @@ def load_file_any(path):
     if path.endswith(".safetensors"):
         from safetensors.torch import load_file
         return load_file(path)
-    return torch.load(path, map_location="cpu")
+    return torch.load(path, map_location="cpu", weights_only=True)      # tensors only: no pickled code
 
 
 def merge_lora(sd, scale=None, lora_alpha=None):

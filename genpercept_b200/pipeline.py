@@ -38,25 +38,33 @@ class GenPerceptOutput:
         return (self.pred_np, self.pred_colored)[k] if isinstance(k, int) else getattr(self, k)
 
 
-def _as_state_dict(m):
+def _as_state_dict(m, variant=None):
     """Accept a module (anything with .state_dict()), a dict, or a path to a checkpoint file/dir."""
     if m is None:
         return None
     if isinstance(m, dict):
         return m
     if isinstance(m, (str, os.PathLike)):
-        return load_checkpoint(m)
+        return load_checkpoint(m, variant)
     if hasattr(m, "state_dict"):
         return m.state_dict()
     raise TypeError(f"cannot take weights from {type(m)}")
 
 
-def load_checkpoint(path):
+def load_checkpoint(path, variant=None):
     """diffusers folder layouts the reference reads (run.py:283-343): a dir holding
-    diffusion_pytorch_model.{safetensors,bin} / model.safetensors, or such a file directly."""
+    diffusion_pytorch_model.{safetensors,bin} / model.safetensors, or such a file directly.  `variant` ("fp16")
+    prefers ``diffusion_pytorch_model.<variant>.safetensors`` like ``from_pretrained(variant=...)`` (run.py:374)."""
     path = str(path)
     if os.path.isdir(path):
-        for n in ("diffusion_pytorch_model.safetensors", "model.safetensors", "diffusion_pytorch_model.bin"):
+        names = []
+        for stem in ("diffusion_pytorch_model", "model"):
+            for ext in ("safetensors", "bin"):
+                if variant:
+                    names.append(f"{stem}.{variant}.{ext}")
+                names.append(f"{stem}.{ext}")
+        names.sort(key=lambda n: (n.endswith(".bin"), variant is None or f".{variant}." not in n))
+        for n in names:
             if os.path.exists(os.path.join(path, n)):
                 path = os.path.join(path, n)
                 break
@@ -65,7 +73,7 @@ def load_checkpoint(path):
     if path.endswith(".safetensors"):
         from safetensors.torch import load_file
         return load_file(path)
-    return torch.load(path, map_location="cpu")
+    return torch.load(path, map_location="cpu", weights_only=True)      # tensors only: no pickled code
 
 
 class GenPerceptPipeline:
@@ -74,7 +82,8 @@ class GenPerceptPipeline:
     def __init__(self, unet, vae, scheduler=None, text_encoder=None, tokenizer=None,
                  default_denoising_steps: Optional[int] = 10, default_processing_resolution: Optional[int] = 768,
                  rgb_blending=False, customized_head=None, genpercept_pipeline=True, *, text_embed=None,
-                 torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None, precision=None):
+                 torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None, precision=None,
+                 variant=None):
         self.genpercept_pipeline = genpercept_pipeline
         if not genpercept_pipeline:
             raise NotImplementedError("only the one-step GenPercept mode (genpercept_pipeline=True) is built; "
@@ -104,8 +113,8 @@ class GenPerceptPipeline:
         self._engine = Engine(dtype=storage, readout="dpt" if customized_head is not None else "vae",
                               timestep=self._timestep, device=device, cuda_graph=cuda_graph, precision=precision)
         self.device = self._engine.device
-        unet_sd = dict(_as_state_dict(unet))
-        vae_sd = W.remap_legacy_vae_keys(_as_state_dict(vae))
+        unet_sd = dict(_as_state_dict(unet, variant))
+        vae_sd = W.remap_legacy_vae_keys(_as_state_dict(vae, variant))
         if customized_head is not None:          # run.py:322-331 drops these for the DPT readout
             unet_sd = {k: v for k, v in unet_sd.items() if not k.startswith(("conv_out", "conv_norm_out"))}
             self._engine.load_state("dpt", _as_state_dict(customized_head))
@@ -130,7 +139,7 @@ class GenPerceptPipeline:
             from transformers import CLIPTextModel, CLIPTokenizer
             kw["text_encoder"] = CLIPTextModel.from_pretrained(os.path.join(root, "text_encoder"))
             kw["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
-        return cls(torch_dtype=torch_dtype, **kw)
+        return cls(torch_dtype=torch_dtype, variant=variant, **kw)
 
     @classmethod
     def from_run_args(cls, checkpoint, unet=None, lora_rank=0, **kw):
@@ -186,49 +195,36 @@ class GenPerceptPipeline:
     def single_infer(self, rgb_in, num_inference_steps=1, generator=None, show_pbar=False, fix_timesteps=None,
                      prompt="", mode=None):
         """rgb_in: [B,3,H,W] uint8 (0..255) or float in [-1,1].  Returns fp32 [B,1|3,H,W] in [0,1] (cuda)."""
-        if fix_timesteps and int(fix_timesteps) != self._timestep:
-            raise ValueError("fix_timesteps is a per-pipeline constant here (folded into the ResNet biases): "
-                             "construct GenPerceptPipeline(..., fix_timesteps=t)")
         assert num_inference_steps == 1, "GenPercept only forward once."
         self._ensure_ready(prompt)
-        mode = mode or getattr(self, "mode", None)
-        ch = 1 if (self.customized_head is not None or mode in ONE_CHANNEL_MODES) else 3
+        # :405-408: a per-call fix_timesteps replaces the scheduler's [1] for THIS call only
+        self._engine.set_timestep(int(fix_timesteps) if fix_timesteps else self._timestep)
+        ch = 1 if (self.customized_head is not None or self._mode(mode) in ONE_CHANNEL_MODES) else 3
         return self._engine.infer(rgb_in, out_channels=ch)
+
+    def _mode(self, mode=None):
+        """``self.mode`` is set by __call__ (:199-200); the helpers read it like the reference does (AttributeError if unset)."""
+        return mode if mode is not None else self.mode
 
     @torch.no_grad()
     def encode_rgb(self, rgb_in):
-        from . import engine as E
+        """:488-505, device-resident (gp_encode): rgb_in [B,3,H,W] uint8 (0..255) or float in [-1,1], cuda or cpu
+        -> latent [B,4,H/8,W/8] on the GPU in ``self.dtype``."""
         self._ensure_ready()
-        B, _, H, W = rgb_in.shape
-        self._engine.plan(B, H, W)
-        x = rgb_in if rgb_in.dtype == torch.uint8 else rgb_in.float()
-        # PRE is part of gp_infer; reuse it by running a full preprocess through write_tensor
-        if x.dtype == torch.uint8:
-            x = x.float() / 255.0 * 2.0 - 1.0
-        self._engine.write_tensor("rgb", x.cpu().numpy())
-        self._engine.run_stage(E.STAGE_VAE_ENCODE)
-        return torch.from_numpy(self._engine.read_tensor("rgb_latent")).to(self.device, self.dtype)
+        return self._engine.encode(rgb_in).to(self.dtype)
 
     @torch.no_grad()
-    def decode_pred(self, pred_latent, post_quant=None):
-        """Returns the decoded map clipped to [-1,1] (the reference clips right after, :470).
-        `post_quant`=(weight[4,4], bias[4]) of vae.post_quant_conv; the engine folded it into the UNet
-        tail, so a caller decoding a *foreign* latent must supply it."""
-        from . import engine as E
+    def decode_pred(self, pred_latent, post_quant=True):
+        """:507-526, device-resident (gp_decode): ``vae.post_quant_conv(pred_latent / 0.18215)`` -> decoder -> channel
+        mean for the one-channel modes, as the reference.  ``post_quant=False`` is for a latent that already went
+        through post_quant_conv (the engine's own "z").  The result is clipped to [-1, 1]: the engine's last kernel
+        fuses the clip the reference applies on the very next line (:470), so values beyond it are not recoverable."""
         if self.customized_head is not None:
             raise ValueError("decode_pred is undefined for the DPT readout")
         self._ensure_ready()
-        z = pred_latent.float().cpu() / self.latent_scale_factor
-        if post_quant is not None:
-            w, b = post_quant
-            z = torch.einsum("oc,bchw->bohw", w.float().reshape(4, 4), z) + b.float().view(1, 4, 1, 1)
-        B, _, h, w_ = z.shape
-        self._engine.plan(B, h * 8, w_ * 8)
-        self._engine.write_tensor("z", z.numpy())
-        ch = 1 if getattr(self, "mode", "depth") in ONE_CHANNEL_MODES else 3
-        self._engine.run_stage(E.STAGE_READOUT, ch)
-        out = self._engine.read_tensor("out").reshape(-1)[:B * ch * h * 8 * w_ * 8].reshape(B, ch, h * 8, w_ * 8)
-        return torch.from_numpy(out * 2.0 - 1.0).to(self.device)
+        ch = 1 if self._mode() in ONE_CHANNEL_MODES else 3
+        out = self._engine.decode(pred_latent.float(), out_channels=ch, post_quant=bool(post_quant))
+        return out * 2.0 - 1.0
 
     @torch.no_grad()
     def __call__(self, input_image, denoising_steps: Optional[int] = None, ensemble_size: int = 1,

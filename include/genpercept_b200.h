@@ -67,17 +67,35 @@ gp_status gp_set_text_embed(gp_engine* e, const float* host_ptr, int n_tokens, i
 /* folds constants, re-packs weights K-major 16-bit, uploads. */
 gp_status gp_finalize(gp_engine* e);
 
-/* builds the static op list, activation arena and (optionally) CUDA graph for one input shape. */
+/* builds the static op list, activation arena and (optionally) CUDA graph for one input shape.  Any H, W >= 32: the
+ * result extent (gp_tensor_shape "out") is 8*floor(H/8) x 8*floor(W/8) for the VAE readout (AutoencoderKL's
+ * stride-2 stages floor) and the DPT head's pyramid extent for the DPT readout; equal to H x W for multiples of 8 / 64. */
 gp_status gp_plan(gp_engine* e, int batch, int height, int width);
+
+/* number of cached plans (the cache is bounded: least-recently-used plans are destroyed; GP_MAX_PLANS, default 4) */
+int gp_plan_count(gp_engine* e);
+/* replaces: the per-call `fix_timesteps` of single_infer (/root/reference/genpercept/genpercept_pipeline.py:405-408).
+ * The timestep only enters through conv1.bias + time_emb_proj(silu(emb(t))) of the 22 UNet ResNets; those biases are
+ * re-folded on the host (cached per timestep) and rewritten in place after a device synchronisation. */
+gp_status gp_set_timestep(gp_engine* e, int timestep);
 
 /* replaces: single_infer.  rgb: [B,3,H,W] NCHW, device (or pinned/pageable host if
  * rgb_on_host != 0; copied on `stream`), dtype GP_U8 (0..255, mapped x/255*2-1 as
  * genpercept_pipeline.py:245) or GP_F16/GP_F32 already in [-1,1].
- * out: fp32 [B,C,H,W] in [0,1], C = out_channels (1: channel-mean modes depth/matting/dis/
+ * out: fp32 [B,C,outH,outW] in [0,1] (a device `out` is written by the last kernel itself), C = out_channels (1: channel-mean modes depth/matting/dis/
  * disparity :523-525; 3: normal/seg); device, or host if out_on_host != 0.  Asynchronous on
  * `stream` unless a host buffer is involved, in which case it returns after the copy. */
 gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, float* out,
                    int out_on_host, int out_channels, void* stream);
+
+/* replaces: encode_rgb (/root/reference/genpercept/genpercept_pipeline.py:488-505).  rgb as for gp_infer; latent_dev:
+ * fp32 [B,4,H/8,W/8] on the device = mean(quant_conv(encoder(rgb))) * 0.18215. */
+gp_status gp_encode(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, float* latent_dev, void* stream);
+/* replaces: decode_pred + clip + shift (:507-526, :470-472).  latent_dev: fp32 [B,4,h,w] on the device (in the scaled
+ * latent space, like the reference's pred_latent); apply_post_quant != 0 applies vae.post_quant_conv to latent / 0.18215 as
+ * the reference always does (0: the latent already went through it, e.g. the engine's own "z").  out_dev: fp32
+ * [B,C,8h,8w] in [0,1] (the reference clips to [-1,1] right after decode_pred, :470; map = out * 2 - 1). */
+gp_status gp_decode(gp_engine* e, const float* latent_dev, int apply_post_quant, float* out_dev, int out_channels, void* stream);
 
 /* Stage entry points for parity tests (each runs a contiguous slice of the planned op list). */
 typedef enum { GP_STAGE_PRE = 0, GP_STAGE_VAE_ENCODE = 1, GP_STAGE_UNET = 2, GP_STAGE_READOUT = 3 } gp_stage;
