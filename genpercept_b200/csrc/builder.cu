@@ -14,6 +14,10 @@ namespace gp {
 size_t Arena::alloc(size_t bytes) {
   bytes = (bytes + 1023) & ~size_t(1023);
   if (bytes == 0) bytes = 1024;
+  // Experiment (GP_ARENA_SKEW=<KiB>): the big VAE tensors are exact multiples of 2^27 bytes, so the input, residual and
+  // output streams of one convolution can sit a power of two apart; a per-allocation skew de-aligns them.
+  static const size_t skew = std::getenv("GP_ARENA_SKEW") ? (size_t)std::atoi(std::getenv("GP_ARENA_SKEW")) * 1024 : 0;
+  if (skew && bytes >= (size_t(1) << 24)) bytes += skew * (1 + (nalloc_++ % 7));
   for (size_t i = 0; i < blks_.size(); ++i) {
     if (blks_[i].free && blks_[i].size >= bytes) {
       if (blks_[i].size > bytes) {
@@ -430,6 +434,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     push(name, 1, flops, bytes, [p](cudaStream_t s) { return igemm_launch(p, s); });
   }
   ops.back().kind = 1;
+  if (a.mode == 3) ops.back().flops_exec = flops * 4.0 / 9.0;      // four 2x2 parity convs instead of a 3x3 on the 2x grid
 }
 
 void Builder::attention_qkv(const std::string& name, const void* q, const void* k, long long cs, const void* vT, int B,

@@ -636,10 +636,29 @@ struct gp_engine {
   }
 
   // encode_rgb: genpercept_pipeline.py:488-505
-  T4 vae_encoder(Builder& b, const T4& rgb8) {
+  T4 vae_encoder(Builder& b, const T4& rgb32) {
     const std::string e = "vae.encoder";
-    T4 x = b.alloc(rgb8.N, rgb8.H, rgb8.W, 128);
-    small_cin_conv(b, e + ".conv_in", rgb8, 3, x);
+    T4 x = b.alloc(rgb32.N, rgb32.H, rgb32.W, 128);
+    {   // conv_in over the K-packed input (preprocess_rgb_im2col): a 1x1 GEMM with K = 27
+      if (!packed.count(e + ".conv_in#im2col")) {
+        const HostT& w = T(e + ".conv_in.weight");
+        GP_REQUIRE(w.shape.size() == 4 && w.shape[0] == 128 && w.shape[1] == 3 && w.shape[2] == 3, e + ".conv_in: unexpected shape");
+        std::vector<float> m((size_t)128 * 32, 0.f);
+        for (int co = 0; co < 128; ++co)
+          for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r)
+              for (int q = 0; q < 3; ++q)
+                m[(size_t)co * 32 + im2col_tap_slot(r, q) * 3 + c] = w.d[(((size_t)co * 3 + c) * 3 + r) * 3 + q];
+        mat_w(e + ".conv_in#im2col", 128, 32, m.data(), T(e + ".conv_in.bias").d);
+      }
+      ConvArgs c;
+      c.srcs = {rgb32};
+      c.ks = 1;
+      c.w = &packed.at(e + ".conv_in#im2col");
+      c.out = x;
+      c.want_stats = true;
+      b.conv(e + ".conv_in", c);
+    }
     const int ch[5] = {128, 128, 256, 512, 512};
     for (int i = 0; i < 4; ++i) {
       for (int j = 0; j < 2; ++j) {
@@ -977,7 +996,7 @@ struct gp_engine {
     const size_t sums_off = b.raw_alloc((size_t)B * 2560 * 2 * 4);
     const size_t ss_off = b.raw_alloc((size_t)B * 2560 * 2 * 4);
     const size_t mm_off = b.raw_alloc((size_t)B * 2 * 4);
-    T4 rgb8 = b.alloc(B, H, W, 8);
+    T4 rgb8 = b.alloc(B, H, W, 32);      // K-packed 3x3 neighbourhoods (preprocess_rgb_im2col); channels 0..2 = the image
     float* out_f32 = nullptr;
     if (!b.measuring()) {
       plan->in_staging = b.raw_ptr(in_off);
@@ -1213,7 +1232,7 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
       GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, npix * 3 * esz, cudaMemcpyHostToDevice, s));
       src = p->in_staging;
     }
-    GP_CUDA(preprocess_rgb(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
+    GP_CUDA(preprocess_rgb_im2col(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
     // 2 = auto: replay a graph where the launch stream is the bottleneck — small plans (measured: +15 % at 384x384,
     // +8 % at 768x768 with one image, nothing at batch 8)
     const bool use_graph = e->cfg.use_cuda_graph == 1 ||
@@ -1268,7 +1287,7 @@ gp_status gp_encode(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_hos
       GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, (size_t)p->B * p->H * p->W * 3 * esz, cudaMemcpyHostToDevice, s));
       src = p->in_staging;
     }
-    GP_CUDA(preprocess_rgb(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
+    GP_CUDA(preprocess_rgb_im2col(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
     GP_CUDA(run_ops(p, GP_STAGE_VAE_ENCODE, GP_STAGE_VAE_ENCODE, 1, s));
     const T4& l = p->kept["rgb_latent"].t;
     GP_CUDA(nhwc8_to_nchw_f32(p->arena + l.off, latent_dev, l.N, l.H, l.W, 4, e->bf16, s, e->split));
@@ -1410,7 +1429,7 @@ gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream) {
 }
 
 gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops, double* bytes,
-                     int* kind) {
+                     int* kind, double* flops_exec) {
   return guarded(e, [&]() {
     Plan* p = e->cur;
     if (!p) throw GpError(GP_ERR_NO_PLAN, "no plan");
@@ -1421,6 +1440,7 @@ gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, d
     if (flops) *flops = op.flops;
     if (bytes) *bytes = op.bytes;
     if (kind) *kind = op.kind;
+    if (flops_exec) *flops_exec = op.flops_exec >= 0 ? op.flops_exec : op.flops;
   });
 }
 
@@ -1720,6 +1740,10 @@ gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int k
     if (flops) *flops = b.ops[0].flops;
   });
 }
+
+/* debug (scripts/patch_trace.py): device buffer of >= 512 int64; CTA 0 of subsequent patch-kernel launches stamps clock64() per K chunk:
+   [i*8+0] transform starts waiting, +1 first patch row landed, +2 transform done; +4 MMA issuer starts waiting, +5 patch ready, +6 taps issued */
+void gp_debug_patch_trace(void* dev_buf) { gp::igemm_patch_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 
 /* debug: device buffer of >= 1024 int64 that CTA 0 of subsequently planned fused-attention launches fills with clock64() stamps */
 void gp_debug_fattn_trace(void* dev_buf) { gp::fattn_set_trace(reinterpret_cast<long long*>(dev_buf)); }

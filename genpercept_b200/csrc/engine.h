@@ -74,6 +74,7 @@ class Arena {
   struct Blk { size_t off, size; bool free; };
   std::vector<Blk> blks_;
   size_t high_ = 0;
+  size_t nalloc_ = 0;
 };
 
 struct Op {
@@ -82,7 +83,8 @@ struct Op {
   int variant = 0;            // 0: always; 1 / 3: only when out_channels matches
   int launches = 1;
   int kind = 0;               // 1: tcgen05 implicit-GEMM launch, 0: anything else
-  double flops = 0, bytes = 0;
+  double flops = 0, bytes = 0;   // algorithmic work: what the reference's op costs
+  double flops_exec = -1;        // MMA work actually issued when it differs (upsample-fused convs run 4 of 9 taps); -1: = flops
   float usec = 0;
   std::function<cudaError_t(cudaStream_t)> run;
 };

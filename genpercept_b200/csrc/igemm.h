@@ -106,12 +106,14 @@ struct IgemmParams {
   CUtensorMap tmPatch2;          // same box over the shortcut source
   // GroupNorm(+SiLU) of the patch source applied in shared memory before the MMA reads it (patch mode only):
   // y = silu(x * scale + shift), (scale, shift) = gn_ss[(image * gn_C + channel) * 2 + {0, 1}] (gn_finalize's output).
+  long long* trace;              // debug (gp_debug_patch_trace): CTA 0 stamps clock64() per K chunk; null = off
   const float* gn_ss;            // null: the source is used as it is
   int gn_C;                      // channels of the normalised tensor (= the patch source's)
   int gn_silu;
 };
 
 cudaError_t igemm_patch_launch(const IgemmParams& p, int grid, cudaStream_t stream);   // igemm_patch.cu
+void igemm_patch_set_trace(long long* dev_buf);   // applies to subsequent launches (debug only)
 
 int igemm_grid(const IgemmParams& p);   // CTAs that igemm_launch will use for p (after igemm_finalize)
 

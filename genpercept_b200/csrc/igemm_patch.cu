@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
       uint32_t a_phase = 0, b_phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int mma_n = 0;
       int tap_off[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((p.seg[0][tap].dy + 1 + h) * kPP + p.seg[0][tap].dx + 1) * 128;
@@ -177,8 +178,12 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride + h * 128;
         for (int kc = 0; kc < kc_all; ++kc) {
+          const bool trm = p.trace != nullptr && blockIdx.x == 0 && h == 0 && leader;
+          const int mix = trm ? mma_n++ : 0;
+          if (trm && mix < 60) p.trace[mix * 8 + 4] = clock64();
           mbar_wait(&a_ready[slot], a_phase, 3);
           tc_fence_after();
+          if (trm && mix < 60) p.trace[mix * 8 + 5] = clock64();
           const uint32_t patch = smem_u32(smem + slot * p.a_slot_bytes);
           if (kc < p.kc_count) {
 #pragma unroll
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
           }
           if (leader) umma_commit(&a_empty[slot]);
           __syncwarp();
+          if (trm && mix < 60) p.trace[mix * 8 + 6] = clock64();
           if (++slot == 2) { slot = 0; a_phase ^= 1; }
         }
         if (leader) umma_commit(&tfull_bar[acc]);
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
     const bool tanh32 = p.gn_silu == 2;              // A/B switch: tanh.approx.f32 instead of the f16x2 form
     int slot = 0;
     uint32_t phase = 0;
+    int trace_n = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int x0 = t.tx * p.TW - 1, y0 = t.ty * p.TH - 1;
@@ -249,6 +256,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
             sc[2 * e] = a.x * pre; sh[2 * e] = a.y * pre; sc[2 * e + 1] = a.z * pre; sh[2 * e + 1] = a.w * pre;
           }
         }
+        const bool trx = p.trace != nullptr && blockIdx.x == 0 && tt == 0;
+        const int tix = trx ? trace_n++ : 0;
+        if (trx && tix < 60) p.trace[tix * 8 + 0] = clock64();
         int landed = 0;                              // patch rows whose barrier this thread has passed
         if (!xf) {
           for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
@@ -260,7 +270,10 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
             bool ok[4];
             {
               const int last = min(r + 48, prows - 1) / kPP;      // deepest patch row this group of four touches
-              for (; landed <= last; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+              for (; landed <= last; ++landed) {
+                mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+                if (trx && tix < 60 && landed == 0) p.trace[tix * 8 + 1] = clock64();
+              }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -293,6 +306,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
           for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);   // keep the phases in step
           fence_proxy_async_shared();                // generic-proxy writes -> visible to the tensor core's reads
         }
+        if (trx && tix < 60) p.trace[tix * 8 + 2] = clock64();
         mbar_arrive(&a_ready[slot]);
         if (++slot == 2) { slot = 0; phase ^= 1; }
       }
@@ -310,7 +324,12 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
 
 }  // namespace
 
-cudaError_t igemm_patch_launch(const IgemmParams& p, int grid, cudaStream_t stream) {
+static long long* g_patch_trace = nullptr;
+void igemm_patch_set_trace(long long* dev_buf) { g_patch_trace = dev_buf; }
+
+cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t stream) {
+  IgemmParams p = p_in;
+  p.trace = g_patch_trace;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

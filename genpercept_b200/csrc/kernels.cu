@@ -576,6 +576,48 @@ __global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_
   store8<BF16>(out + i * (lo ? 16 : 8), lo, f);
 }
 
+// K-packed stem: the 3x3 neighbourhood of every pixel laid out along the channel axis, NHWC32 =
+// [centre tap (3 ch) | the other 8 taps in row-major order (24 ch) | 5 zeros], so that AutoencoderKL.encoder.conv_in
+// (3 -> 128, 3x3) becomes a 1x1 GEMM with K = 27 (one 64-channel chunk) instead of nine 64-wide chunks of which 3
+// channels are real (1177 us -> one pass bound by the 1.2 GB output write at 8 x 768^2).  Out-of-image taps are zero.
+template <bool BF16>
+__global__ void preprocess_im2col_kernel(const void* __restrict__ in, int kind, uint16_t* __restrict__ out, int N, int H, int W,
+                                         int lo) {
+  const long long HW = (long long)H * W;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  const int n = (int)(i / HW);
+  const long long p = i % HW;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float f[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) f[k] = 0.f;
+  auto fetch = [&](int yy, int xx, int c) -> float {
+    if ((unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) return 0.f;
+    const long long off = ((long long)n * 3 + c) * HW + (long long)yy * W + xx;
+    if (kind == 0) return (float)reinterpret_cast<const uint8_t*>(in)[off] / 255.0f * 2.0f - 1.0f;
+    if (kind == 1) return f16_to_f32<false>(reinterpret_cast<const uint16_t*>(in)[off]);
+    return reinterpret_cast<const float*>(in)[off];
+  };
+  int slot = 1;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int k = (r == 1 && q == 1) ? 0 : slot++;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[k * 3 + c] = fetch(y + r - 1, x + q - 1, c);
+    }
+  uint16_t* o = out + i * (lo ? 64 : 32);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = f[v * 8 + e];
+    store8<BF16>(o + v * 8, lo, g);
+  }
+}
+
 __device__ __forceinline__ unsigned int f2ord(float f) {
   unsigned int u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -839,6 +881,13 @@ cudaError_t nchw4_affine_to_nhwc8(const float* in, void* out, int N, int H, int 
   const long long HW = (long long)H * W, total = (long long)N * HW;
   GP_DISPATCH_BF16(bf16, (nchw4_affine_to_nhwc8_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
                              in, reinterpret_cast<uint16_t*>(out), N, HW, pre, m, b, split ? 8 : 0)));
+  return cudaGetLastError();
+}
+
+cudaError_t preprocess_rgb_im2col(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s, bool split) {
+  const long long total = (long long)N * H * W;
+  GP_DISPATCH_BF16(bf16, (preprocess_im2col_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+                             in, in_kind, reinterpret_cast<uint16_t*>(out), N, H, W, split ? 32 : 0)));
   return cudaGetLastError();
 }
 

@@ -75,6 +75,15 @@ cudaError_t preprocess_rgb(const void* in, int in_kind /*0 u8, 1 f16, 2 f32*/, v
 cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, int c, bool bf16, cudaStream_t s, bool split = false);
 cudaError_t nchw4_affine_to_nhwc8(const float* in, void* out, int N, int H, int W, float pre, const float* m /*[4][4] or null*/,
                                   const float* b /*[4] or null*/, bool bf16, cudaStream_t s, bool split = false);
+// Same input as preprocess_rgb, K-packed for the VAE encoder's stem: 16-bit NHWC32 = the pixel's 3x3 neighbourhood along
+// the channel axis [centre tap | 8 other taps row-major | 5 zeros]; im2col_tap_slot(r, q) gives a tap's position.
+cudaError_t preprocess_rgb_im2col(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s,
+                                  bool split = false);
+inline int im2col_tap_slot(int r, int q) {      // 3x3 tap (r, q) -> group of 3 channels inside the NHWC32 pixel
+  if (r == 1 && q == 1) return 0;
+  const int lin = r * 3 + q;
+  return lin < 4 ? lin + 1 : lin;
+}
 // per-image (x - min) / (max - min) over HW fp32 values, in place; scratch: 2 uint32 per image.
 cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s);
 

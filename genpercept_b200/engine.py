@@ -60,7 +60,7 @@ def lib():
                                POINTER(c_double)]
     L.gp_profile_ops.argtypes = [c_void_p, c_int, c_void_p]
     L.gp_op_info.argtypes = [c_void_p, c_int64, c_char_p, c_size_t, POINTER(c_double), POINTER(c_double),
-                             POINTER(c_double), POINTER(c_int)]
+                             POINTER(c_double), POINTER(c_int), POINTER(c_double)]
     L.gp_conv2d.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_int, c_void_p]
     L.gp_groupnorm.argtypes = [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
@@ -237,11 +237,11 @@ class Engine:
         self._ck(self.L.gp_profile_ops(self.h, out_channels, self._sp()), "gp_profile_ops")
         res = []
         buf = ctypes.create_string_buffer(256)
-        us, fl, by, kd = c_double(), c_double(), c_double(), c_int()
+        us, fl, by, kd, fx = c_double(), c_double(), c_double(), c_int(), c_double()
         for i in range(self.plan_info()["ops"]):
-            self._ck(self.L.gp_op_info(self.h, i, buf, 256, byref(us), byref(fl), byref(by), byref(kd)), "gp_op_info")
+            self._ck(self.L.gp_op_info(self.h, i, buf, 256, byref(us), byref(fl), byref(by), byref(kd), byref(fx)), "gp_op_info")
             res.append({"name": buf.value.decode(), "usec": us.value, "flops": fl.value, "bytes": by.value,
-                        "kind": kd.value})
+                        "kind": kd.value, "flops_exec": fx.value})
         return res
 
 

@@ -84,15 +84,15 @@ def resolve_unet_checkpoint(unet_dir, checkpoint_path):
     return osp.join(str(checkpoint_path), "unet", "diffusion_pytorch_model.safetensors"), decoder_dir
 
 
-def assemble(checkpoint_path, unet=None, lora_rank=0):
+def assemble(checkpoint_path, unet=None, lora_rank=0, variant=None):
     """-> dict(unet=state_dict, vae=state_dict, customized_head=state_dict | None) for GenPerceptPipeline.
 
     `checkpoint_path`: SD-2.1 folder; `unet`: the reference's ``--unet`` argument (None = base UNet)."""
     checkpoint_path = str(checkpoint_path)
     head = None
-    vae = W.remap_legacy_vae_keys(_load_dir(osp.join(checkpoint_path, "vae")))
+    vae = W.remap_legacy_vae_keys(_load_dir(osp.join(checkpoint_path, "vae"), variant))
     if unet is None:
-        unet_sd = _load_dir(osp.join(checkpoint_path, "unet"))
+        unet_sd = _load_dir(osp.join(checkpoint_path, "unet"), variant)
         return {"unet": unet_sd, "vae": vae, "customized_head": None}
     unet_file, decoder_dir = resolve_unet_checkpoint(unet, checkpoint_path)
     if decoder_dir:
@@ -118,8 +118,13 @@ def assemble(checkpoint_path, unet=None, lora_rank=0):
     return {"unet": unet_sd, "vae": vae, "customized_head": head}
 
 
-def _load_dir(path):
-    for n in ("diffusion_pytorch_model.safetensors", "model.safetensors", "diffusion_pytorch_model.bin"):
+def _load_dir(path, variant=None):
+    """`variant` ("fp16"): prefer diffusion_pytorch_model.<variant>.safetensors, like from_pretrained(variant=...) (run.py:374)."""
+    names = ["diffusion_pytorch_model.safetensors", "model.safetensors", "diffusion_pytorch_model.bin"]
+    if variant:
+        names = [f"diffusion_pytorch_model.{variant}.safetensors", f"model.{variant}.safetensors",
+                 f"diffusion_pytorch_model.{variant}.bin"] + names
+    for n in names:
         p = osp.join(path, n)
         if osp.exists(p):
             return load_file_any(p)

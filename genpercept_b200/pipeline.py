@@ -148,7 +148,7 @@ class GenPerceptPipeline:
         ``dpt_head_identity/`` or ``vae_decoder/`` + ``vae_post_quant_conv/`` next to it) and ``--lora_rank``.
         See genpercept_b200/loader.py for the layouts."""
         from . import loader
-        parts = loader.assemble(checkpoint, unet=unet, lora_rank=lora_rank)
+        parts = loader.assemble(checkpoint, unet=unet, lora_rank=lora_rank, variant=kw.get("variant"))
         root = str(checkpoint)
         if kw.get("text_embed") is None and kw.get("text_encoder") is None and os.path.isdir(os.path.join(root, "text_encoder")):
             from transformers import CLIPTextModel, CLIPTokenizer

@@ -111,9 +111,10 @@ gp_status gp_plan_info(gp_engine* e, int64_t* n_ops, int64_t* n_kernel_launches,
                        int64_t* weight_bytes, double* igemm_flops);
 /* name/us of the i-th op after gp_profile_ops ran the plan once with CUDA events per op. */
 gp_status gp_profile_ops(gp_engine* e, int out_channels, void* stream);
-/* kind: 1 = tcgen05 implicit-GEMM launch, 0 = other kernels */
+/* kind: 1 = tcgen05 implicit-GEMM launch, 2 = fused attention, 0 = other kernels.  flops = algorithmic work of the op
+ * (SURVEY.md 8d); flops_exec = MMA work actually issued (differs for the upsample-fused convolutions: 4 of 9 taps). */
 gp_status gp_op_info(gp_engine* e, int64_t i, char* name_buf, size_t name_cap, double* usec, double* flops,
-                     double* bytes, int* kind);
+                     double* bytes, int* kind, double* flops_exec);
 
 /* ---- per-kernel entry points (parity tests, micro-benchmarks); all pointers are device ---- */
 /* 3x3 / 1x1 convolution through the tcgen05 implicit-GEMM kernel.  x: 16-bit NHWC [N,H,W,Cin];
@@ -163,6 +164,10 @@ gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int k
 /* debug (scripts/fattn_trace.py): a device buffer of >= 1024 int64 that CTA 0 of the fused-attention launches planned
  * afterwards fills with clock64() stamps at its phase boundaries; NULL switches the stamps off again. */
 void gp_debug_fattn_trace(void* dev_buf);
+/* debug (scripts/patch_trace.py): a device buffer of >= 512 int64 that CTA 0 of the patch-resident kernel launches made
+ * afterwards fills with clock64() stamps per K chunk (transform: wait / first row landed / done; MMA issuer: wait / ready /
+ * issued); NULL switches the stamps off. */
+void gp_debug_patch_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

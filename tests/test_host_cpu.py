@@ -62,3 +62,34 @@ def test_legacy_vae_key_remap():
     out = remap_legacy_vae_keys(sd)
     assert out["encoder.mid_block.attentions.0.to_q.weight"].shape == (512, 512)
     assert "encoder.mid_block.attentions.0.to_out.0.bias" in out and "encoder.conv_in.weight" in out
+
+
+def test_dropin_seeds_the_reference_import_path(tmp_path):
+    """run.py:33 does `from genpercept import GenPerceptPipeline`; genpercept/__init__.py:18 resolves it through
+    `.genpercept_pipeline`.  With genpercept_b200.dropin installed, an UNMODIFIED reference-style package hands out this
+    repo's classes (its own genpercept_pipeline.py — which needs diffusers — is never executed) while its other
+    submodules still resolve on disk."""
+    import subprocess
+    import sys
+    pkg = tmp_path / "genpercept"
+    (pkg / "util").mkdir(parents=True)
+    (pkg / "__init__.py").write_text("from .genpercept_pipeline import GenPerceptPipeline, GenPerceptOutput\n")
+    (pkg / "genpercept_pipeline.py").write_text("import diffusers_that_is_not_installed\n")
+    (pkg / "util" / "__init__.py").write_text("")
+    (pkg / "util" / "image_util.py").write_text("MARK = 'reference util'\n")
+    (tmp_path / "run.py").write_text(
+        "import sys\nfrom genpercept import GenPerceptPipeline, GenPerceptOutput\nfrom genpercept.util.image_util import MARK\n"
+        "print(GenPerceptPipeline.__module__, GenPerceptOutput.__module__, MARK, sys.argv[1:])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "genpercept_b200.dropin", "run.py", "--mode", "depth"], cwd=tmp_path,
+                       env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "genpercept_b200.pipeline genpercept_b200.pipeline reference util ['--mode', 'depth']" in p.stdout
+    ref = "/root/reference"
+    if os.path.isdir(os.path.join(ref, "genpercept")):        # and against the real checkout where it exists (not on the GPU box)
+        code = ("import genpercept_b200.dropin as d; d.install(); from genpercept import GenPerceptPipeline as P; "
+                "import genpercept; print(P.__module__, genpercept.__file__)")
+        q = subprocess.run([sys.executable, "-c", code], cwd=ref, env=dict(os.environ, PYTHONPATH=root), capture_output=True,
+                           text=True, timeout=300)
+        assert q.returncode == 0, q.stderr[-2000:]
+        assert "genpercept_b200.pipeline /root/reference/genpercept/__init__.py" in q.stdout
