@@ -111,6 +111,22 @@ static int choose_bn(int cout, int force) {
   if (force) return force;
   const int c16 = ceil_div(cout, 16) * 16;
   if (c16 <= 256) return c16;
+  // Cout = 320 / 640 (the SD-2.1 UNet's first two levels): an exact divisor (160) is not a multiple of 64 and forces the
+  // direct epilogue (16-byte stores at a 2*Cout-byte stride, per-thread residual rows, no GroupNorm statistics).  A
+  // multiple of 64 keeps the staged TMA-store epilogue even if the last N tile is partly empty: 640 = 5 x 128 exactly,
+  // 320 -> 2 x 192 (64 idle columns).  GP_BN_POLICY=0 restores the divisor rule (A/B switch).
+  static const int policy = std::getenv("GP_BN_POLICY") ? std::atoi(std::getenv("GP_BN_POLICY")) : 1;
+  if (policy && (cout % 64) == 0) {
+    for (int bn : {256, 192, 128})
+      if (cout % bn == 0) return bn;
+    if (policy == 2) return 128;
+    int best = 256, best_pad = 1 << 30;
+    for (int bn : {256, 192, 128}) {
+      const int pad = ceil_div(cout, bn) * bn - cout;
+      if (pad < best_pad) { best_pad = pad; best = bn; }
+    }
+    return best;
+  }
   for (int bn = 256; bn >= 128; bn -= 16)
     if (cout % bn == 0) return bn;
   const int n = ceil_div(cout, 256);

@@ -108,6 +108,8 @@ struct gp_engine {
   std::vector<void*> dev_allocs;
   size_t weight_bytes = 0;
   float* pq_dev = nullptr;   // vae.post_quant_conv: [16] weight + [4] bias, fp32 on the device
+  bool multistep = false;    // cfg.arch == 1: real DDIM steps around the UNet, no scheduler fold
+  int unet_in_ch = 0;        // 4, or 8 for the marigold arch (cat([rgb_latent, pred_latent]))
   std::vector<float> temb;   // [1280] time embedding for the current timestep
   // Per-call fix_timesteps (genpercept_pipeline.py:405-408): the timestep only enters through
   // conv1.bias + time_emb_proj(silu(emb(t))) of the 22 UNet ResNets, so changing it re-folds those biases in place
@@ -710,7 +712,14 @@ struct gp_engine {
     compute_temb();
     const std::string u = "unet";
     T4 x = b.alloc(lat8.N, lat8.H, lat8.W, 320);
-    small_cin_conv(b, u + ".conv_in", lat8, 4, x);
+    // conv_in takes 4 channels (GenPercept, rgb_blending) or 8 = cat([rgb_latent, pred_latent]) (run.py:59-78, --archs marigold)
+    if (unet_in_ch == 0) {
+      const HostT& wci = T(u + ".conv_in.weight");
+      GP_REQUIRE(wci.shape.size() == 4 && (wci.shape[1] == 4 || wci.shape[1] == 8), "unet.conv_in must take 4 or 8 channels");
+      unet_in_ch = (int)wci.shape[1];
+      GP_REQUIRE(multistep || unet_in_ch == 4, "an 8-channel conv_in belongs to the multi-step arch (gp_config.arch = 1)");
+    }
+    small_cin_conv(b, u + ".conv_in", lat8, unet_in_ch, x);
     std::vector<T4> skips = {x};
     int cin = 320;
     for (int i = 0; i < 4; ++i) {
@@ -808,6 +817,30 @@ struct gp_engine {
       }
     }
     if (want_feats) {
+      b.release(cur);
+      return;
+    }
+    if (multistep) {   // the scheduler step is a real one: conv_out as it is (model_output), DDIM + post_quant_conv run outside
+      if (pq_dev == nullptr) {
+        std::vector<float> pqm = T("vae.post_quant_conv.weight").d;
+        const std::vector<float>& pqb = T("vae.post_quant_conv.bias").d;
+        pqm.insert(pqm.end(), pqb.begin(), pqb.end());
+        pq_dev = upload(pqm);
+      }
+      if (!packed.count("unet.conv_out#plain")) {
+        const HostT &w = T(u + ".conv_out.weight"), &bb = T(u + ".conv_out.bias");
+        folded["unet.conv_out#plain"].assign((size_t)8 * 320 * 9, 0.f);
+        std::vector<float>& f = folded["unet.conv_out#plain"];
+        std::copy(w.d.begin(), w.d.begin() + (size_t)4 * 320 * 9, f.begin());
+        std::vector<float> bias(8, 0.f);
+        for (int o = 0; o < 4; ++o) bias[o] = bb.d[o];
+        std::vector<SegSpec> segs;
+        for (int r = 0; r < 9; ++r) { SegSpec sg; sg.C = 320; sg.terms.push_back(Term{f.data() + r, 320 * 9, 9, 1.f}); segs.push_back(sg); }
+        packed.emplace("unet.conv_out#plain", pack({segs}, 8, bias));
+      }
+      ConvArgs c; c.srcs = {cur}; c.w = &packed.at("unet.conv_out#plain"); c.out = *z_out;
+      c.gn = &norm_w(u + ".conv_norm_out"); c.gn_name = u + ".conv_norm_out"; c.gn_eps = 1e-5f;
+      b.conv("unet.conv_out", c);
       b.release(cur);
       return;
     }
@@ -1015,7 +1048,17 @@ struct gp_engine {
     const bool dpt = cfg.readout == GP_READOUT_DPT;
     T4 feats[4];
     T4 z = b.alloc(B, latent.H, latent.W, 8);
-    unet(b, latent, dpt, &z, feats);
+    T4 xin{}, sample{}, npred{}, x0{};
+    if (multistep) {
+      GP_REQUIRE(!dpt, "the multi-step archs decode with the VAE (the reference's DPT readout is one-step)");
+      xin = b.alloc(B, latent.H, latent.W, 8);      // the UNet's input of a step
+      sample = b.alloc(B, latent.H, latent.W, 8);   // pred_latent
+      npred = b.alloc(B, latent.H, latent.W, 8);    // model_output
+      x0 = b.alloc(B, latent.H, latent.W, 8);       // pred_original_sample
+      unet(b, xin, false, &npred, feats);
+    } else {
+      unet(b, latent, dpt, &z, feats);
+    }
     b.stage = GP_STAGE_READOUT;
     int oh = 8 * latent.H, ow = 8 * latent.W;
     if (dpt) dpt_head(b, feats, out_f32, mm, &oh, &ow);
@@ -1026,6 +1069,12 @@ struct gp_engine {
       plan->kept["rgb"] = Kept{rgb8, nullptr, 3};
       plan->kept["rgb_latent"] = Kept{latent, nullptr, 4};
       if (!dpt) plan->kept["z"] = Kept{z, nullptr, 4};
+      if (multistep) {
+        plan->kept["xin"] = Kept{xin, nullptr, 8};
+        plan->kept["sample"] = Kept{sample, nullptr, 4};
+        plan->kept["noise_pred"] = Kept{npred, nullptr, 4};
+        plan->kept["x0"] = Kept{x0, nullptr, 4};
+      }
       if (dpt)
         for (int i = 0; i < 4; ++i) plan->kept["feat" + std::to_string(i)] = Kept{feats[i], nullptr, feats[i].C};
     }
@@ -1080,6 +1129,8 @@ gp_status gp_create(const gp_config* cfg, gp_engine** out) {
   if (e->cfg.timestep <= 0) e->cfg.timestep = 1;
   e->bf16 = cfg->dtype == GP_BF16;
   e->split = cfg->precision == 1;
+  e->multistep = cfg->arch == 1;
+  if (cfg->arch != 0 && cfg->arch != 1) { delete e; return GP_ERR_INVALID; }
   if (cfg->precision != 0 && cfg->precision != 1) { delete e; return GP_ERR_INVALID; }
   *out = e;
   return GP_OK;
@@ -1182,10 +1233,16 @@ gp_status gp_plan(gp_engine* e, int B, int H, int W) {
 
 int gp_plan_count(gp_engine* e) { return e ? (int)e->plans.size() : 0; }
 
+static void set_timestep_now(gp_engine* e, int timestep);
+
 gp_status gp_set_timestep(gp_engine* e, int timestep) {
-  return guarded(e, [&]() {
+  return guarded(e, [&]() { set_timestep_now(e, timestep); });
+}
+
+static void set_timestep_now(gp_engine* e, int timestep) {
+  {
     if (!e->finalized) throw GpError(GP_ERR_STATE, "gp_set_timestep before gp_finalize");
-    GP_REQUIRE(timestep >= 1 && timestep <= 1000, "gp_set_timestep: timestep must be in [1, 1000]");
+    GP_REQUIRE(timestep >= 0 && timestep <= 1000, "gp_set_timestep: timestep must be in [0, 1000]");
     if (timestep == e->cur_timestep) return;
     GP_CUDA(cudaSetDevice(e->cfg.device));
     auto it = e->temb_cache.find(timestep);
@@ -1204,7 +1261,7 @@ gp_status gp_set_timestep(gp_engine* e, int timestep) {
     for (size_t i = 0; i < e->temb_layers.size(); ++i)
       GP_CUDA(cudaMemcpy(e->temb_layers[i].dev_bias, it->second[i].data(), (size_t)e->temb_layers[i].cout * 4, cudaMemcpyHostToDevice));
     e->cur_timestep = timestep;
-  });
+  }
 }
 
 gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, float* out, int out_on_host,
@@ -1212,6 +1269,7 @@ gp_status gp_infer(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host
   return guarded(e, [&]() {
     Plan* p = e->cur;
     if (!p) throw GpError(GP_ERR_NO_PLAN, "gp_infer: no plan (call gp_plan)");
+    if (e->multistep) throw GpError(GP_ERR_STATE, "gp_infer: this engine runs the multi-step arch (gp_infer_steps)");
     const bool dpt = e->cfg.readout == GP_READOUT_DPT;
     if (dpt) out_channels = 1;
     GP_REQUIRE(rgb && out && (out_channels == 1 || out_channels == 3), "gp_infer: bad arguments");
@@ -1310,6 +1368,62 @@ gp_status gp_decode(gp_engine* e, const float* latent_dev, int apply_post_quant,
     p->out_dst = out_dev;
     GP_CUDA(run_ops(p, GP_STAGE_READOUT, GP_STAGE_READOUT, out_channels, s));
     p->out_dst = p->out_f32;
+  });
+}
+
+gp_status gp_infer_steps(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, const float* noise, int noise_on_host,
+                         const int* timesteps, const float* coeffs, int n_steps, float* out, int out_on_host, int out_channels,
+                         void* stream) {
+  return guarded(e, [&]() {
+    Plan* p = e->cur;
+    if (!p) throw GpError(GP_ERR_NO_PLAN, "gp_infer_steps: no plan (call gp_plan)");
+    if (!e->multistep) throw GpError(GP_ERR_STATE, "gp_infer_steps needs gp_config.arch = 1");
+    GP_REQUIRE(rgb && out && timesteps && coeffs && n_steps >= 1 && (out_channels == 1 || out_channels == 3), "gp_infer_steps: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    GP_CUDA(cudaSetDevice(e->cfg.device));
+    p->last_used = ++e->use_clock;
+    int kind = 0;
+    size_t esz = 1;
+    if (rgb_dtype == GP_U8) { kind = 0; esz = 1; }
+    else if (rgb_dtype == GP_F16) { kind = 1; esz = 2; }
+    else if (rgb_dtype == GP_F32) { kind = 2; esz = 4; }
+    else throw GpError(GP_ERR_INVALID, "gp_infer_steps: rgb dtype must be u8, f16 or f32");
+    const void* src = rgb;
+    if (rgb_on_host) {
+      GP_CUDA(cudaMemcpyAsync(p->in_staging, rgb, (size_t)p->B * p->H * p->W * 3 * esz, cudaMemcpyHostToDevice, s));
+      src = p->in_staging;
+    }
+    GP_CUDA(preprocess_rgb_im2col(src, kind, p->arena + p->kept["rgb"].t.off, p->B, p->H, p->W, e->bf16, s, e->split));
+    GP_CUDA(run_ops(p, GP_STAGE_VAE_ENCODE, GP_STAGE_VAE_ENCODE, out_channels, s));      // rgb_latent (:416)
+    const T4& lat = p->kept["rgb_latent"].t;
+    const long long npx = lat.pixels();
+    uint8_t* A = p->arena;
+    void* smp = A + p->kept["sample"].t.off;
+    if (noise) {              // marigold: pred_latent = randn (:418-425; the caller draws it with its generator)
+      const float* nd = noise;
+      if (noise_on_host) {    // the plan's result buffer is free until the decoder runs
+        GP_CUDA(cudaMemcpyAsync(p->out_f32, noise, (size_t)npx * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+        nd = p->out_f32;
+      }
+      GP_CUDA(nchw4_affine_to_nhwc8(nd, smp, lat.N, lat.H, lat.W, 1.0f, nullptr, nullptr, e->bf16, s, e->split));
+    } else {                  // rgb_blending: pred_latent = rgb_latent (:426-427)
+      GP_CUDA(cudaMemcpyAsync(smp, A + lat.off, lat.bytes(), cudaMemcpyDeviceToDevice, s));
+    }
+    for (int i = 0; i < n_steps; ++i) {                                                  // :443-463
+      GP_CUDA(latent_pack(A + lat.off, smp, A + p->kept["xin"].t.off, npx, e->unet_in_ch, e->bf16, s, e->split));
+      set_timestep_now(e, timesteps[i]);
+      GP_CUDA(run_ops(p, GP_STAGE_UNET, GP_STAGE_UNET, out_channels, s));
+      GP_CUDA(ddim_step(A + p->kept["noise_pred"].t.off, smp, A + p->kept["x0"].t.off, npx, coeffs + 4 * i, e->bf16, s, e->split));
+    }
+    // pred_latent = step_output.pred_original_sample (:465); decode_pred (:507-526); clip + shift in the last kernel
+    GP_CUDA(latent_affine(A + p->kept["x0"].t.off, A + p->kept["z"].t.off, npx, 1.0f / kLatentScale, e->pq_dev, e->pq_dev + 16,
+                          e->bf16, s, e->split));
+    p->out_dst = out_on_host ? p->out_f32 : out;
+    GP_CUDA(run_ops(p, GP_STAGE_READOUT, GP_STAGE_READOUT, out_channels, s));
+    if (p->out_dst != out)
+      GP_CUDA(cudaMemcpyAsync(out, p->out_f32, (size_t)p->B * p->outH * p->outW * out_channels * 4, cudaMemcpyDeviceToHost, s));
+    p->out_dst = p->out_f32;
+    if (rgb_on_host || out_on_host) GP_CUDA(cudaStreamSynchronize(s));
   });
 }
 
@@ -1686,6 +1800,27 @@ gp_status gp_attention(int dtype, const void* q, const void* k, const void* v, i
     b.attention_qkv("attn", qs, k, C, vT, B, T, heads, d, nullptr, b.external(o, B, 1, T, C));
     run_all(b, s);
     GP_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+gp_status gp_ensemble_reduce(const float* pred_dev, int B, int H, int W, const float* scale_host, const float* shift_host,
+                             int median, int normalise, float* out_dev, void* stream) {
+  return guarded_free([&]() {
+    GP_REQUIRE(pred_dev && out_dev && scale_host && shift_host && B >= 1 && B <= 32, "gp_ensemble_reduce: bad arguments (B <= 32)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    float* ss = nullptr;
+    GP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss), (size_t)(2 * B + 2) * sizeof(float)));
+    cudaError_t err = cudaMemcpyAsync(ss, scale_host, (size_t)B * 4, cudaMemcpyHostToDevice, s);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(ss + B, shift_host, (size_t)B * 4, cudaMemcpyHostToDevice, s);
+    const long long HW = (long long)H * W;
+    if (err == cudaSuccess) err = ensemble_reduce(pred_dev, B, HW, ss, ss + B, median != 0, out_dev, s);
+    // (depth - min) / (max - min).clamp(1e-6), or depth / max for scale-only alignment (ensemble.py:193-201)
+    if (err == cudaSuccess && normalise)
+      err = minmax_normalize(out_dev, 1, HW, reinterpret_cast<unsigned int*>(ss + 2 * B), s, 1e-6f, normalise == 2);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(ss);
+    GP_CUDA(err);
+    GP_CUDA(e2);
   });
 }
 

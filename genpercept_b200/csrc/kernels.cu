@@ -639,10 +639,10 @@ __global__ void minmax_reduce_kernel(const float* __restrict__ x, long long HW, 
   mn = -warp_max(-mn); mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) { atomicMin(&s[2 * n], f2ord(mn)); atomicMax(&s[2 * n + 1], f2ord(mx)); }
 }
-__global__ void minmax_apply_kernel(float* __restrict__ x, long long HW, const unsigned int* __restrict__ s) {
+__global__ void minmax_apply_kernel(float* __restrict__ x, long long HW, const unsigned int* __restrict__ s, float dmin, int zero_min) {
   const int n = blockIdx.y;
-  const float mn = ord2f(s[2 * n]), mx = ord2f(s[2 * n + 1]);
-  const float d = mx - mn;
+  const float mn = zero_min ? 0.f : ord2f(s[2 * n]), mx = ord2f(s[2 * n + 1]);
+  const float d = fmaxf(mx - mn, dmin);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
     x[(long long)n * HW + i] = (x[(long long)n * HW + i] - mn) / d;
 }
@@ -869,6 +869,86 @@ __global__ void nchw4_affine_to_nhwc8_kernel(const float* __restrict__ in, uint1
 }
 }  // namespace
 
+namespace {
+// Latent-space glue of the multi-step archs, all on 16-bit NHWC8 latents (4 real channels).
+// unet_input = cat([rgb_latent, pred_latent]) for the 8-channel conv_in (genpercept_pipeline.py:446-449), else pred_latent.
+template <bool BF16>
+__global__ void latent_pack_kernel(const uint16_t* __restrict__ lat, const uint16_t* __restrict__ smp, uint16_t* __restrict__ xin,
+                                   long long npx, int in_ch, int lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npx) return;
+  const long long o = i * (lo ? 16 : 8);
+  float a[8], b[8], f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  load8<BF16>(smp + o, lo, b);
+  if (in_ch == 8) {
+    load8<BF16>(lat + o, lo, a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[k] = a[k]; f[4 + k] = b[k]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = b[k];
+  }
+  store8<BF16>(xin + o, lo, f);
+}
+// DDIMScheduler.step with eta = 0: x0 = c0 * sample + c1 * model_output, prev_sample = c2 * sample + c3 * model_output
+// (genpercept_b200/scheduler.py step_coefficients); prev_sample overwrites `smp`.
+template <bool BF16>
+__global__ void ddim_step_kernel(const uint16_t* __restrict__ mo, uint16_t* __restrict__ smp, uint16_t* __restrict__ x0, long long npx,
+                                 float c0, float c1, float c2, float c3, int lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npx) return;
+  const long long o = i * (lo ? 16 : 8);
+  float m[8], x[8], p0[8], pv[8];
+  load8<BF16>(mo + o, lo, m);
+  load8<BF16>(smp + o, lo, x);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    p0[k] = k < 4 ? c0 * x[k] + c1 * m[k] : 0.f;
+    pv[k] = k < 4 ? c2 * x[k] + c3 * m[k] : 0.f;
+  }
+  store8<BF16>(x0 + o, lo, p0);
+  store8<BF16>(smp + o, lo, pv);
+}
+// z = M (x * pre) + b on NHWC8 latents (post_quant_conv(pred_latent / 0.18215), genpercept_pipeline.py:519-521)
+template <bool BF16>
+__global__ void latent_affine_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long npx, float pre,
+                                     const float* __restrict__ mat, const float* __restrict__ bias, int lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npx) return;
+  const long long o = i * (lo ? 16 : 8);
+  float x[8], f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  load8<BF16>(in + o, lo, x);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float a = bias ? bias[r] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a = fmaf(mat[r * 4 + k], x[k] * pre, a);
+    f[r] = a;
+  }
+  store8<BF16>(out + o, lo, f);
+}
+}  // namespace
+
+cudaError_t latent_pack(const void* lat, const void* smp, void* xin, long long npx, int in_ch, bool bf16, cudaStream_t s, bool split) {
+  GP_DISPATCH_BF16(bf16, (latent_pack_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(lat), reinterpret_cast<const uint16_t*>(smp),
+                             reinterpret_cast<uint16_t*>(xin), npx, in_ch, split ? 8 : 0)));
+  return cudaGetLastError();
+}
+cudaError_t ddim_step(const void* model_out, void* sample, void* x0, long long npx, const float c[4], bool bf16, cudaStream_t s, bool split) {
+  GP_DISPATCH_BF16(bf16, (ddim_step_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(model_out), reinterpret_cast<uint16_t*>(sample),
+                             reinterpret_cast<uint16_t*>(x0), npx, c[0], c[1], c[2], c[3], split ? 8 : 0)));
+  return cudaGetLastError();
+}
+cudaError_t latent_affine(const void* in, void* out, long long npx, float pre, const float* mat, const float* bias, bool bf16,
+                          cudaStream_t s, bool split) {
+  GP_DISPATCH_BF16(bf16, (latent_affine_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+                             reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), npx, pre, mat, bias,
+                             split ? 8 : 0)));
+  return cudaGetLastError();
+}
+
 cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, int c, bool bf16, cudaStream_t s, bool split) {
   const long long HW = (long long)H * W, total = (long long)N * HW;
   GP_DISPATCH_BF16(bf16, (nhwc8_to_nchw_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
@@ -891,13 +971,40 @@ cudaError_t preprocess_rgb_im2col(const void* in, int in_kind, void* out, int N,
   return cudaGetLastError();
 }
 
-cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s) {
+cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s, float dmin, bool zero_min) {
   minmax_init_kernel<<<(N + 63) / 64, 64, 0, s>>>(scratch, N);
   int bx = (int)((HW + 256 * 8 - 1) / (256 * 8));
   if (bx > 256) bx = 256;
   if (bx < 1) bx = 1;
   minmax_reduce_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch);
-  minmax_apply_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch);
+  minmax_apply_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch, dmin, zero_min ? 1 : 0);
+  return cudaGetLastError();
+}
+
+namespace {
+// Test-time ensembling (genpercept/util/ensemble.py:117-156,190-191): members aligned by (scale, shift), then the per-pixel
+// median (torch.median: the LOWER middle value for an even count) or mean.
+__global__ void ensemble_reduce_kernel(const float* __restrict__ d, int B, long long HW, const float* __restrict__ sc,
+                                       const float* __restrict__ sh, int median, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  float v[32];
+  float sum = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float x = __fadd_rn(__fmul_rn(d[(long long)b * HW + i], sc[b]), sh[b]);   // torch: mul, then add (no FMA)
+    sum += x;
+    int j = b;                                   // insertion sort (B <= 32)
+    while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; }
+    v[j] = x;
+  }
+  out[i] = median ? v[(B - 1) / 2] : sum / (float)B;
+}
+}  // namespace
+
+cudaError_t ensemble_reduce(const float* d, int B, long long HW, const float* scale_dev, const float* shift_dev, bool median, float* out,
+                            cudaStream_t s) {
+  if (B < 1 || B > 32) return cudaErrorInvalidValue;
+  ensemble_reduce_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s>>>(d, B, HW, scale_dev, shift_dev, median ? 1 : 0, out);
   return cudaGetLastError();
 }
 

@@ -84,7 +84,18 @@ inline int im2col_tap_slot(int r, int q) {      // 3x3 tap (r, q) -> group of 3 
   const int lin = r * 3 + q;
   return lin < 4 ? lin + 1 : lin;
 }
+// Multi-step archs, 16-bit NHWC8 latents: the UNet input of a step (in_ch 8: [rgb_latent | pred_latent],
+// 4: pred_latent), the DDIM update (eta = 0; coefficients from genpercept_b200/scheduler.py) and post_quant_conv(x / 0.18215).
+cudaError_t latent_pack(const void* lat, const void* smp, void* xin, long long npx, int in_ch, bool bf16, cudaStream_t s, bool split = false);
+cudaError_t ddim_step(const void* model_out, void* sample, void* x0, long long npx, const float c[4], bool bf16, cudaStream_t s,
+                      bool split = false);
+cudaError_t latent_affine(const void* in, void* out, long long npx, float pre, const float* mat, const float* bias, bool bf16,
+                          cudaStream_t s, bool split = false);
 // per-image (x - min) / (max - min) over HW fp32 values, in place; scratch: 2 uint32 per image.
-cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s);
+// dmin: lower clamp of (max - min) (0 for the DPT readout, 1e-6 in ensemble_depth); zero_min: normalise by max only
+cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s, float dmin = 0.f, bool zero_min = false);
+// out[HW] = median / mean over the B <= 32 members of d[B][HW] * scale[b] + shift[b]  (genpercept/util/ensemble.py)
+cudaError_t ensemble_reduce(const float* d, int B, long long HW, const float* scale_dev, const float* shift_dev, bool median, float* out,
+                            cudaStream_t s);
 
 }  // namespace gp

@@ -23,7 +23,7 @@ _STATUS = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_MISSING", 3: "GP_ERR_NO_P
 
 class _Config(ctypes.Structure):
     _fields_ = [("device", c_int), ("dtype", c_int), ("readout", c_int), ("timestep", c_int),
-                ("use_cuda_graph", c_int), ("precision", c_int)]
+                ("use_cuda_graph", c_int), ("precision", c_int), ("arch", c_int)]
 
 
 _lib = None
@@ -52,6 +52,9 @@ def lib():
     L.gp_encode.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.gp_decode.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
     L.gp_set_timestep.argtypes = [c_void_p, c_int]
+    L.gp_infer_steps.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, POINTER(c_int), POINTER(c_float), c_int, c_void_p,
+                                 c_int, c_int, c_void_p]
+    L.gp_ensemble_reduce.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.gp_plan_count.argtypes = [c_void_p]
     L.gp_tensor_shape.argtypes = [c_void_p, c_char_p, POINTER(c_int64)]
     L.gp_read_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
@@ -100,7 +103,7 @@ class Engine:
     """One engine per (process, GPU).  Mirrors the C-ABI one to one."""
 
     def __init__(self, dtype=torch.float16, readout="vae", timestep=1, device=0, cuda_graph="auto",
-                 precision="default"):
+                 precision="default", arch="genpercept"):
         if not torch.cuda.is_available():
             raise RuntimeError("genpercept_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.L = lib()
@@ -109,8 +112,9 @@ class Engine:
         self.device = torch.device("cuda", device)
         cfg = _Config(device, _gp_dtype(dtype), GP_READOUT_DPT if readout == "dpt" else GP_READOUT_VAE, timestep,
                       2 if cuda_graph == "auto" else (1 if cuda_graph else 0),   # auto: graphs for small plans
-                      {"default": 0, "high": 1}[precision])
+                      {"default": 0, "high": 1}[precision], {"genpercept": 0, "multistep": 1}[arch])
         self.precision = precision
+        self.arch = arch
         self.h = c_void_p()
         st = self.L.gp_create(byref(cfg), byref(self.h))
         if st != 0:
@@ -209,6 +213,30 @@ class Engine:
                                  c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, C, self._sp()), "gp_infer")
         return out
 
+    def infer_steps(self, rgb, timesteps, coeffs, noise=None, out_channels=1, out=None):
+        """Multi-step archs (gp_infer_steps): `timesteps` [n] ints, `coeffs` [n,4] DDIM coefficients
+        (scheduler.DDIMSchedule.step_coefficients), `noise` fp32 [B,4,h,w] (marigold) or None (rgb_blending)."""
+        assert rgb.dim() == 4 and rgb.shape[1] == 3
+        B, _, H, W = rgb.shape
+        if self.plan_shape != (B, H, W):
+            self.plan(B, H, W)
+        rgb = (rgb.float() if rgb.dtype == torch.bfloat16 else rgb).contiguous()
+        Ho, Wo = self.out_hw
+        if out is None:
+            out = torch.empty((B, out_channels, Ho, Wo), dtype=torch.float32, device=self.device)
+        n = len(timesteps)
+        ts = (c_int * n)(*[int(t) for t in timesteps])
+        cf = (c_float * (4 * n))(*[float(v) for row in coeffs for v in row])
+        nz = None
+        if noise is not None:
+            nz = noise.detach().to(torch.float32).contiguous()
+            assert tuple(nz.shape) == (B, 4) + tuple(self.tensor_shape("rgb_latent")[2:]), "noise must be [B,4,H/8,W/8]"
+        self._ck(self.L.gp_infer_steps(self.h, c_void_p(rgb.data_ptr()), _gp_dtype(rgb.dtype), 0 if rgb.is_cuda else 1,
+                                       c_void_p(nz.data_ptr()) if nz is not None else None, 0 if (nz is None or nz.is_cuda) else 1,
+                                       ts, cf, n, c_void_p(out.data_ptr()), 0 if out.is_cuda else 1, out_channels, self._sp()),
+                 "gp_infer_steps")
+        return out
+
     def run_stage(self, stage, out_channels=1):
         self._ck(self.L.gp_run_stage(self.h, stage, out_channels, self._sp()), "gp_run_stage")
 
@@ -302,6 +330,20 @@ def gn_conv3x3(x_nhwc, groups, gamma, beta, eps, silu, w, bias=None, sc_x=None, 
                              pp(residual), pp(y), 1 if out_f32 else 0, _stream_ptr())
     _check_free(st, "gp_gn_conv3x3")
     return y
+
+
+def ensemble_reduce(pred, scale, shift, median=True, normalise=1):
+    """gp_ensemble_reduce: pred fp32 [B,1,H,W] (cuda) -> [1,1,H,W] (cuda); scale / shift: numpy [B]."""
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.dim() == 4 and pred.shape[1] == 1
+    pred = pred.contiguous()
+    B, _, H, W = pred.shape
+    sc = np.ascontiguousarray(scale, dtype=np.float32)
+    sh = np.ascontiguousarray(shift, dtype=np.float32)
+    out = torch.empty((1, 1, H, W), dtype=torch.float32, device=pred.device)
+    st = lib().gp_ensemble_reduce(c_void_p(pred.data_ptr()), B, H, W, sc.ctypes.data_as(c_void_p), sh.ctypes.data_as(c_void_p),
+                                  1 if median else 0, int(normalise), c_void_p(out.data_ptr()), _stream_ptr(pred.device))
+    _check_free(st, "gp_ensemble_reduce")
+    return out
 
 
 def layernorm(x, gamma, beta, eps=1e-5):

@@ -85,14 +85,27 @@ class GenPerceptPipeline:
                  torch_dtype=torch.float16, device=0, cuda_graph="auto", fix_timesteps=None, precision=None,
                  variant=None):
         self.genpercept_pipeline = genpercept_pipeline
-        if not genpercept_pipeline:
-            raise NotImplementedError("only the one-step GenPercept mode (genpercept_pipeline=True) is built; "
-                                      "multi-step Marigold / rgb_blending archs are SURVEY.md 8(f4)")
-        default_denoising_steps = 1
-        rgb_blending = True
-        if scheduler is not None and hasattr(scheduler, "beta_start"):
-            assert scheduler.beta_start == 1 and scheduler.beta_end == 1, \
-                "the one-step collapse x0 = -v needs the beta=1 scheduler (hf_configs/scheduler_beta_1.0_1.0)"
+        if genpercept_pipeline:                       # genpercept_pipeline.py:122-125
+            default_denoising_steps = 1
+            rgb_blending = True
+            cfg = getattr(scheduler, "config", scheduler)
+            bs = cfg.get("beta_start") if isinstance(cfg, dict) else getattr(cfg, "beta_start", None)
+            be = cfg.get("beta_end") if isinstance(cfg, dict) else getattr(cfg, "beta_end", None)
+            if bs is not None:
+                assert bs == 1 and be == 1, \
+                    "the one-step collapse x0 = -v needs the beta=1 scheduler (hf_configs/scheduler_beta_1.0_1.0)"
+        else:
+            # multi-step archs (run.py --archs marigold / rgb_blending): real DDIM steps around the UNet.
+            # `scheduler`: a scheduler_config.json path / folder / dict, a DDIMSchedule, or any object whose .config
+            # carries the reference's scheduler fields (the reference passes its DDIMSchedulerCustomized).
+            from .scheduler import DDIMSchedule
+            if customized_head is not None:
+                raise ValueError("the DPT readout is one-step (genpercept_pipeline.py:474-483)")
+            if scheduler is None:
+                raise ValueError("the multi-step archs need a scheduler (hf_configs/scheduler_beta_*/scheduler_config.json)")
+            if not isinstance(scheduler, DDIMSchedule):
+                cfg = getattr(scheduler, "config", scheduler)
+                scheduler = DDIMSchedule.from_config(dict(cfg) if not isinstance(cfg, (str, os.PathLike)) else cfg)
         self.scheduler = scheduler
         self.text_encoder = text_encoder
         self.tokenizer = tokenizer
@@ -111,7 +124,8 @@ class GenPerceptPipeline:
         storage = torch.bfloat16 if self.dtype == torch.bfloat16 else torch.float16
         self._timestep = int(fix_timesteps) if fix_timesteps else 1
         self._engine = Engine(dtype=storage, readout="dpt" if customized_head is not None else "vae",
-                              timestep=self._timestep, device=device, cuda_graph=cuda_graph, precision=precision)
+                              timestep=self._timestep, device=device, cuda_graph=cuda_graph, precision=precision,
+                              arch="genpercept" if genpercept_pipeline else "multistep")
         self.device = self._engine.device
         unet_sd = dict(_as_state_dict(unet, variant))
         vae_sd = W.remap_legacy_vae_keys(_as_state_dict(vae, variant))
@@ -195,12 +209,29 @@ class GenPerceptPipeline:
     def single_infer(self, rgb_in, num_inference_steps=1, generator=None, show_pbar=False, fix_timesteps=None,
                      prompt="", mode=None):
         """rgb_in: [B,3,H,W] uint8 (0..255) or float in [-1,1].  Returns fp32 [B,1|3,H,W] in [0,1] (cuda)."""
+        if not self.genpercept_pipeline:
+            return self._single_infer_steps(rgb_in, num_inference_steps, generator, fix_timesteps, prompt, mode)
         assert num_inference_steps == 1, "GenPercept only forward once."
         self._ensure_ready(prompt)
         # :405-408: a per-call fix_timesteps replaces the scheduler's [1] for THIS call only
         self._engine.set_timestep(int(fix_timesteps) if fix_timesteps else self._timestep)
         ch = 1 if (self.customized_head is not None or self._mode(mode) in ONE_CHANNEL_MODES) else 3
         return self._engine.infer(rgb_in, out_channels=ch)
+
+    def _single_infer_steps(self, rgb_in, num_inference_steps, generator, fix_timesteps, prompt, mode):
+        """genpercept_pipeline.py:399-472 with genpercept_pipeline=False: set_timesteps, pred_latent = randn (marigold) or
+        rgb_latent (rgb_blending), the denoising loop with the scheduler's DDIM step, decode(pred_original_sample)."""
+        self._ensure_ready(prompt)
+        ts = self.scheduler.set_timesteps(int(num_inference_steps))
+        coeffs = [self.scheduler.step_coefficients(t) for t in ts]           # the step always uses the schedule's t (:459)
+        t_unet = [int(fix_timesteps)] * len(ts) if fix_timesteps else [int(t) for t in ts]   # :405-408
+        B, _, H, W = rgb_in.shape
+        noise = None
+        if not self.rgb_blending:                                            # :418-425
+            gdev = generator.device if generator is not None else self.device
+            noise = torch.randn((B, 4, H // 8, W // 8), device=gdev, dtype=torch.float32, generator=generator)
+        ch = 1 if self._mode(mode) in ONE_CHANNEL_MODES else 3
+        return self._engine.infer_steps(rgb_in, t_unet, coeffs, noise=noise, out_channels=ch)
 
     def _mode(self, mode=None):
         """``self.mode`` is set by __call__ (:199-200); the helpers read it like the reference does (AttributeError if unset)."""
@@ -239,8 +270,11 @@ class GenPerceptPipeline:
             processing_res = self.default_processing_resolution
         assert processing_res >= 0
         assert ensemble_size >= 1
-        assert ensemble_size == 1
-        assert denoising_steps == 1
+        if self.genpercept_pipeline:                  # :211-213
+            assert ensemble_size == 1
+            assert denoising_steps == 1
+        else:
+            assert denoising_steps >= 1
         resample = get_tv_resample_method(resample_method)
         if isinstance(input_image, Image.Image):
             rgb = pil_to_tensor(input_image.convert("RGB")).unsqueeze(0)
@@ -266,8 +300,22 @@ class GenPerceptPipeline:
         if rgb.dtype != torch.uint8:                       # float image in [0,255]: the reference keeps it float (:245)
             rgb = rgb.to(self.device) / 255.0 * 2.0 - 1.0
         # for uint8 the normalisation x/255*2-1 and the cast to self.dtype (:245-246) happen inside the engine
-        pred = self.single_infer(rgb, num_inference_steps=denoising_steps, generator=generator,
-                                 show_pbar=show_progress_bar, fix_timesteps=fix_timesteps, prompt=prompt, mode=mode)
+        if self.genpercept_pipeline or ensemble_size == 1:
+            pred = self.single_infer(rgb, num_inference_steps=denoising_steps, generator=generator,
+                                     show_pbar=show_progress_bar, fix_timesteps=fix_timesteps, prompt=prompt, mode=mode)
+        else:
+            # :250-296: the image repeated ensemble_size times, inferred in batches, then ensemble_depth
+            assert rgb.shape[0] == 1, "ensembling takes one image (the reference expands it ensemble_size times)"
+            from .ensemble import ensemble_depth
+            bs = batch_size if batch_size > 0 else min(ensemble_size, 8)
+            members = []
+            for lo in range(0, ensemble_size, bs):
+                n = min(bs, ensemble_size - lo)
+                members.append(self.single_infer(rgb.expand(n, -1, -1, -1), num_inference_steps=denoising_steps,
+                                                 generator=generator, show_pbar=show_progress_bar, fix_timesteps=fix_timesteps,
+                                                 prompt=prompt, mode=mode))
+            pred, _ = ensemble_depth(torch.cat(members, dim=0), scale_invariant=True, shift_invariant=True, max_res=50,
+                                     **(ensemble_kwargs or {}))
         if match_input_res and tuple(pred.shape[-2:]) != tuple(input_size[-2:]):
             if gpu_resample:
                 pred = E.resize_aa(pred, int(input_size[-2]), int(input_size[-1]), resample_method)

@@ -194,7 +194,7 @@ def _synth(spec, gen, gain=1.0, out_gain=None):
     return sd
 
 
-def synth_state(seed=1234, with_dpt=True):
+def synth_state(seed=1234, with_dpt=True, unet_in_channels=4):
     """Seeded synthetic fp32 weights with the exact SD-2.1 topology.
 
     Gains are chosen so activations stay O(1) through the depth of the graph and the final maps
@@ -203,7 +203,7 @@ def synth_state(seed=1234, with_dpt=True):
     state = {
         "vae": _synth(vae_spec(), gen, gain=1.0,
                       out_gain={"decoder.conv_out": 1.5, "encoder.conv_out": 2.0, "quant_conv": 1.5}),
-        "unet": _synth(unet_spec(), gen, gain=1.0, out_gain={"conv_out": 2.0}),
+        "unet": _synth(unet_spec(in_channels=unet_in_channels), gen, gain=1.0, out_gain={"conv_out": 2.0}),
     }
     if with_dpt:
         state["dpt"] = _synth(dpt_spec(), gen, gain=1.0)

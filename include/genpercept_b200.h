@@ -48,6 +48,9 @@ typedef struct {
                             1: high — every activation and weight is carried as an fp16 (hi, lo) pair and every
                             contraction runs hi*hi + lo*hi + hi*lo on the tensor cores (fp32-class products,
                             fp32 accumulate): the reference's default fp32 run (run.py:273-281)              */
+  int arch;              /* 0: one-step GenPercept (the scheduler's beta = 1 step folded into the UNet tail);
+                            1: multi-step (run.py --archs marigold / rgb_blending): the UNet returns model_output, real
+                            DDIM steps run around it (gp_infer_steps); conv_in may take 8 channels (run.py:59-78)   */
 } gp_config;
 
 /* replaces: GenPerceptPipeline.__init__/from_pretrained model assembly (run.py:314-376) */
@@ -97,6 +100,15 @@ gp_status gp_encode(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_hos
  * [B,C,8h,8w] in [0,1] (the reference clips to [-1,1] right after decode_pred, :470; map = out * 2 - 1). */
 gp_status gp_decode(gp_engine* e, const float* latent_dev, int apply_post_quant, float* out_dev, int out_channels, void* stream);
 
+/* replaces: single_infer for the multi-step archs (/root/reference/genpercept/genpercept_pipeline.py:399-472; gp_config.arch = 1):
+ *   rgb_latent = encode_rgb(rgb); pred_latent = noise (marigold; fp32 [B,4,h,w], host or device) or rgb_latent (noise == NULL:
+ *   rgb_blending); per step i: unet(cat([rgb_latent, pred_latent]) or pred_latent, timesteps[i]) -> DDIM step with
+ *   coeffs[4 i .. 4 i + 3] = (x0 <- sample, x0 <- model_output, prev <- sample, prev <- model_output) (eta = 0; host
+ *   arrays, genpercept_b200/scheduler.py); then decode_pred(pred_original_sample), clip, shift.  out as for gp_infer. */
+gp_status gp_infer_steps(gp_engine* e, const void* rgb, int rgb_dtype, int rgb_on_host, const float* noise, int noise_on_host,
+                         const int* timesteps, const float* coeffs, int n_steps, float* out, int out_on_host, int out_channels,
+                         void* stream);
+
 /* Stage entry points for parity tests (each runs a contiguous slice of the planned op list). */
 typedef enum { GP_STAGE_PRE = 0, GP_STAGE_VAE_ENCODE = 1, GP_STAGE_UNET = 2, GP_STAGE_READOUT = 3 } gp_stage;
 gp_status gp_run_stage(gp_engine* e, int stage, int out_channels, void* stream);
@@ -139,6 +151,11 @@ gp_status gp_layernorm(int dtype, const void* x, int64_t tokens, int C, const fl
 /* softmax(q k^T * scale) v per (batch, head); q,k,v,o: 16-bit [B,T,heads*d] */
 gp_status gp_attention(int dtype, const void* q, const void* k, const void* v, int B, int T, int heads, int d,
                        float scale, void* o, void* stream);
+/* replaces: the align / reduce / normalise tail of ensemble_depth (/root/reference/genpercept/util/ensemble.py:101-156,
+ * 186-203): out[H,W] = median (torch.median: lower middle) or mean over the B <= 32 members of pred[b] * scale[b] + shift[b],
+ * then (normalise 1) (x - min) / max(max - min, 1e-6) or (normalise 2) x / max(max, 1e-6).  pred / out: fp32 on the device. */
+gp_status gp_ensemble_reduce(const float* pred_dev, int B, int H, int W, const float* scale_host, const float* shift_host,
+                             int median, int normalise, float* out_dev, void* stream);
 gp_status gp_bilinear_up2x(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
 /* ---- pre/post-processing around the hot path; buffers may be host or device ------------
  * gp_resize_aa replaces torchvision.transforms.functional.resize(tensor, size, interpolation, antialias=True)
