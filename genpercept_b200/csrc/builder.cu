@@ -418,6 +418,8 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
       p.gn_C = s0.C;
       static const bool tanh32 = std::getenv("GP_PATCH_TANH32") != nullptr;     // A/B switch
       p.gn_silu = a.gn_silu ? (tanh32 ? 2 : 1) : 0;
+      static const int xmode = std::getenv("GP_PATCH_XFORM") ? std::atoi(std::getenv("GP_PATCH_XFORM")) : 0;
+      p.gn_mode = xmode;
     }
   }
   if (emit_stats) {

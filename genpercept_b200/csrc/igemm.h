@@ -110,6 +110,7 @@ struct IgemmParams {
   const float* gn_ss;            // null: the source is used as it is
   int gn_C;                      // channels of the normalised tensor (= the patch source's)
   int gn_silu;
+  int gn_mode;                   // experiment switches of the transform loop (GP_PATCH_XFORM), see igemm_patch.cu
 };
 
 cudaError_t igemm_patch_launch(const IgemmParams& p, int grid, cudaStream_t stream);   // igemm_patch.cu

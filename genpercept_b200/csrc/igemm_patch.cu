@@ -262,7 +262,36 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
         int landed = 0;                              // patch rows whose barrier this thread has passed
         if (!xf) {
           for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+        } else if (p.gn_mode & 2) {                  // experiment: one row per iteration after the whole patch has landed
+          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+          const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
+          int py = 0, px = rbase;
+          for (int r = rbase; r < prows; r += 16) {
+            const bool inside = px < kPW && (unsigned)(y0 + py) < (unsigned)p.gridH && (unsigned)(x0 + px) < (unsigned)p.gridW;
+            if (inside) {
+              const uint32_t addr = base + r * 128;
+              uint32_t w[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = fmaf(cvt16<BF16>((uint16_t)(w[e] & 0xFFFF)), sc[2 * e], sh[2 * e]);
+                float b = fmaf(cvt16<BF16>((uint16_t)(w[e] >> 16)), sc[2 * e + 1], sh[2 * e + 1]);
+                if (BF16 || tanh32) {
+                  if (do_silu) { a = silu_tanh(a); b = silu_tanh(b); }
+                  w[e] = pack16<BF16>(a, b);
+                } else {
+                  w[e] = do_silu ? silu_pair_f16(a, b) : pack16<BF16>(a, b);
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
+            px += 16;
+            if (px >= kPP) { px -= kPP; ++py; }
+          }
+          fence_proxy_async_shared();
         } else {
+          if (p.gn_mode & 1)                         // experiment: start only when the whole patch has landed
+            for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
           const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
           int py = 0, px = rbase;                    // rbase < 16 < kPW
           for (int r = rbase; r < prows; r += 64) {  // four rows in flight per thread
