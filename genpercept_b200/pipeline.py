@@ -223,8 +223,9 @@ class GenPerceptPipeline:
         rgb_latent (rgb_blending), the denoising loop with the scheduler's DDIM step, decode(pred_original_sample)."""
         self._ensure_ready(prompt)
         ts = self.scheduler.set_timesteps(int(num_inference_steps))
-        coeffs = [self.scheduler.step_coefficients(t) for t in ts]           # the step always uses the schedule's t (:459)
-        t_unet = [int(fix_timesteps)] * len(ts) if fix_timesteps else [int(t) for t in ts]   # :405-408
+        # :405-408: fix_timesteps replaces EVERY timestep of the loop — the UNet's and the scheduler step's (:453-460)
+        t_unet = [int(fix_timesteps)] * len(ts) if fix_timesteps else [int(t) for t in ts]
+        coeffs = [self.scheduler.step_coefficients(t) for t in t_unet]
         B, _, H, W = rgb_in.shape
         noise = None
         if not self.rgb_blending:                                            # :418-425

@@ -8,10 +8,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# fp16 storage / fp32 accumulate through ~110 GEMM-class layers.  Measured on B200 (round 1):
-# rgb_latent 1.2e-3 (|ref|<=0.87), z 4.5e-2 (|ref|<=17.6, i.e. 2.5e-3 relative), final maps see DESIGN.md.
-# z is unnormalised (std 5), so its bound is relative to max|ref|.
-TOL = {"rgb_latent": 4e-3, "z_rel": 6e-3, "out": 1e-2}
+# fp16 storage / fp32 accumulate through ~110 GEMM-class layers.  Measured on B200 (round 2, the small cases of this file):
+# rgb_latent 1.6e-3 (|ref|<=0.87), z 5.2e-2 (|ref|<=17.6, i.e. 3.0e-3 relative; unnormalised, std 5: bounded relative to
+# max|ref|), depth max 3.0e-3 .. 5.8e-3 (mean 5.2e-4 .. 7.6e-4), normal max 5.7e-3 .. 9.8e-3 (mean 7.3e-4 .. 9.2e-4).
+# The bounds sit ~1.3x above the largest value measured; the full-size cases and the high-precision mode (|delta| < 1e-3)
+# are in tests/test_gpu_fullsize.py.
+TOL = {"rgb_latent": 4e-3, "z_rel": 6e-3, "depth": 8e-3, "normal": 1.3e-2}
 
 
 def _report(name, got, ref):
@@ -54,8 +56,8 @@ def test_vae_readout_matches_golden_and_oracle(engines, synth_state, text_embed,
     z_ref = p.vae.post_quant_conv(-torch.from_numpy(g["unet_out"]) / LATENT_SCALE).detach().numpy()
     assert _report("rgb_latent", lat, g["rgb_latent"]) < TOL["rgb_latent"]
     assert _report("z (decoder input)", z, z_ref) < TOL["z_rel"] * np.abs(z_ref).max()
-    assert _report("depth", depth, g["depth"]) < TOL["out"]
-    assert _report("normal", normal, g["normal"]) < TOL["out"]
+    assert _report("depth", depth, g["depth"]) < TOL["depth"]
+    assert _report("normal", normal, g["normal"]) < TOL["normal"]
     assert depth.min() >= 0 and depth.max() <= 1
 
 
@@ -74,7 +76,7 @@ def test_stage_isolation_unet_and_decoder(engines, synth_state, text_embed, gold
     e.write_tensor("z", z_ref)
     e.run_stage(E.STAGE_READOUT, 1)
     out = e.read_tensor("out").reshape(-1)[:2 * 64 * 64].reshape(2, 1, 64, 64)   # packed [B,1,H,W]
-    assert _report("decoder stage", out, g["depth"]) < TOL["out"]
+    assert _report("decoder stage", out, g["depth"]) < TOL["depth"]
 
 
 def test_dpt_readout_matches_golden(engines, golden_dir):
@@ -82,7 +84,7 @@ def test_dpt_readout_matches_golden(engines, golden_dir):
     e = engines["dpt"]
     rgb = torch.from_numpy(g["rgb"]).cuda()
     out = e.infer(rgb).cpu().numpy()
-    assert _report("dpt", out, g["dpt"]) < 2e-2
+    assert _report("dpt", out, g["dpt"]) < 8e-3          # measured 3.9e-3
     assert abs(out.min()) < 1e-6 and abs(out.max() - 1) < 1e-6     # per-image min-max
 
 
@@ -145,8 +147,8 @@ def test_sizes_that_are_multiples_of_8_only(engines, synth_state, text_embed, hw
     ref_d = p.single_infer(x, mode="depth").numpy()
     ref_n = p.single_infer(x, mode="normal").numpy()
     assert depth.shape == (2, 1, H, W) and normal.shape == (2, 3, H, W)
-    assert _report(f"depth {H}x{W}", depth, ref_d) < TOL["out"]
-    assert _report(f"normal {H}x{W}", normal, ref_n) < TOL["out"]
+    assert _report(f"depth {H}x{W}", depth, ref_d) < TOL["depth"]
+    assert _report(f"normal {H}x{W}", normal, ref_n) < TOL["normal"]
     # sizes that are not multiples of 8 / 64 run too (tests/test_gpu_boundary.py); the result extent follows the graph
     assert tuple(e.infer(torch.zeros((1, 3, 68, 64), dtype=torch.uint8, device="cuda")).shape) == (1, 1, 64, 64)
     assert tuple(engines["dpt"].infer(torch.zeros((1, 3, 72, 64), dtype=torch.uint8, device="cuda")).shape) == (1, 1, 96, 64)
@@ -171,7 +173,7 @@ def test_general_context_length(synth_state, text_embed, ntok):
     finally:
         e.close()
     ref = OraclePipeline(synth_state, te).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
-    assert _report(f"depth, {ntok}-token context", depth, ref) < TOL["out"]
+    assert _report(f"depth, {ntok}-token context", depth, ref) < TOL["depth"]
     # the context matters: the 2-token empty-prompt result is a different map
     ref2 = OraclePipeline(synth_state, text_embed).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
     print("   |oracle(n tokens) - oracle(empty prompt)| max", float(np.abs(ref - ref2).max()))
@@ -210,6 +212,31 @@ def test_high_precision_mode_meets_the_stated_tolerance(synth_state, text_embed,
             e.close()
 
 
+def test_groupnorm_fused_graph_matches_the_oracle(synth_state, text_embed, monkeypatch):
+    """GP_GN_FUSE=1: the GroupNorm passes of the W % 128 == 0 VAE layers run inside the consuming convolutions
+    (igemm_patch.cu); same tolerances as the default graph.  256x384: 256- and 384-wide layers take the fused path."""
+    from genpercept_b200.engine import Engine
+    from oracle.pipeline import OraclePipeline
+    monkeypatch.setenv("GP_GN_FUSE", "1")
+    g = torch.Generator().manual_seed(31)
+    rgb = torch.randint(0, 256, (2, 3, 128, 256), generator=g, dtype=torch.uint8)
+    e = Engine(dtype=torch.float16, readout="vae")
+    try:
+        e.load_state("unet", synth_state["unet"]); e.load_state("vae", synth_state["vae"])
+        e.set_text_embed(text_embed)
+        e.finalize()
+        depth = e.infer(rgb.cuda(), out_channels=1).cpu().numpy()
+        normal = e.infer(rgb.cuda(), out_channels=3).cpu().numpy()
+        names = [o["name"] for o in e.profile_ops(out_channels=1)]
+    finally:
+        e.close()
+    assert "vae.decoder.up_blocks.3.resnets.0.norm1" in names                     # scale/shift op only: no gn_apply output tensor
+    p = OraclePipeline(synth_state, text_embed)
+    x = rgb.float() / 255.0 * 2.0 - 1.0
+    assert _report("fused-GN depth", depth, p.single_infer(x, mode="depth").numpy()) < TOL["depth"]
+    assert _report("fused-GN normal", normal, p.single_infer(x, mode="normal").numpy()) < TOL["normal"]
+
+
 def test_mid_size_against_the_oracle(engines, synth_state, text_embed):
     """256x384, batch 2: the largest size the CPU oracle finishes in seconds; exercises the patch-resident conv
     loop (W % 128 == 0), multi-block attention (T = 1536) and the TMA residual path with full tiles."""
@@ -219,7 +246,7 @@ def test_mid_size_against_the_oracle(engines, synth_state, text_embed):
     depth = engines["vae"].infer(rgb.cuda(), out_channels=1).cpu().numpy()
     torch.set_num_threads(min(16, torch.get_num_threads()))
     ref = OraclePipeline(synth_state, text_embed).single_infer(rgb.float() / 255.0 * 2.0 - 1.0, mode="depth").numpy()
-    assert _report("depth 256x384", depth, ref) < TOL["out"]
+    assert _report("depth 256x384", depth, ref) < TOL["depth"]
 
 
 def test_full_size_properties(engines):

@@ -149,11 +149,14 @@ def test_groupnorm(shape, groups, silu):
     dict(N=1, H=24, W=96, Cin=128, Cout=128),                      # W % 128 != 0: GroupNorm pass + tap-streaming conv
     dict(N=1, H=16, W=128, Cin=128, Cout=128, silu=False),
 ])
-def test_groupnorm_fused_into_conv3x3(case):
-    """GroupNorm(32)+SiLU applied in the convolution's operand path (igemm_patch.cu) against F.group_norm -> F.silu ->
-    F.conv2d on the same 16-bit inputs.  The fused kernel rounds the normalised operand to 16 bit exactly like the
-    two-pass form does (it is the same arithmetic on a patch in shared memory), so the single-op bound applies."""
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_groupnorm_fused_into_conv3x3(case, fuse, monkeypatch):
+    """GroupNorm(32)+SiLU applied in the convolution's operand path (igemm_patch.cu, GP_GN_FUSE=1) and as a GroupNorm pass
+    followed by the convolution (the default), against F.group_norm -> F.silu -> F.conv2d on the same 16-bit inputs.
+    The fused kernel rounds the normalised operand to 16 bit exactly like the two-pass form does (it is the same
+    arithmetic on a patch in shared memory), so the single-op bound applies to both."""
     from genpercept_b200 import engine as E
+    monkeypatch.setenv("GP_GN_FUSE", fuse)
     _setup()
     N, H, W, Cin, Cout = (case[k] for k in ("N", "H", "W", "Cin", "Cout"))
     Csc, silu = case.get("Csc"), case.get("silu", True)
