@@ -381,6 +381,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     // the residual has the output's shape and addressing: same maps over its base
     if (a.res1 && !a.res2 && !(a.flags & IG_GEGLU) && !split_ && std::getenv("GP_NO_RES_TMA") == nullptr) {
       p.res_tma = 1;
+      p.res_prefetch = std::getenv("GP_NO_RES_PREFETCH") == nullptr ? 1 : 0;
       const void* rb = ptr(*a.res1);
       if (tokens) {
         const long long ntok = (long long)N * H * W;

@@ -147,6 +147,20 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
     const int cls = p.cls_from_z0 ? t.z0 : 0;
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
+    // The residual boxes of this CTA's NEXT tile are pulled into L2 now, a whole tile period before their TMA loads:
+    // those loads sit serially in front of every 32 x 64 piece of the epilogue, and with DRAM latency (1.5 us under
+    // load) four of them per warp outlast the main loop of the short-K (Cout = 128) layers (r2: residual convs 20-30 %
+    // slower than plain ones; the main loop of a 128->128 tile is 6 us).
+    if (p.res_prefetch && lane == 0 && tile + (int)gridDim.x < p.total_tiles) {
+      const TileCoord tn = decode_tile(p, tile + gridDim.x);
+      const int ncls = p.cls_from_z0 ? tn.z0 : 0;
+      for (int h = 0; h < p.MT; ++h) {
+        const int r0 = h * 128 + wq * 32;
+        const int psx = tn.tx * p.TW + (r0 & (p.TW - 1)), psy = tn.ty * p.TH + (r0 >> p.tw_shift);
+        for (int c0 = 0; c0 < p.BN && tn.n_tile * p.BN + c0 < p.Cout; c0 += 64)
+          tma_prefetch_l2_4d(&p.tmRes[ncls], tn.n_tile * p.BN + c0, psx, psy, tn.z1);
+      }
+    }
     if (do_stats) {
       const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
       if (img != cur_img) {

@@ -60,8 +60,11 @@ __device__ __forceinline__ uint32_t silu_pair_f16(float ha, float hb) {     // i
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
+// XFORM = false: no transform warpgroup (256 threads, the full register budget for the epilogue warps — the 384-thread
+// build caps every thread at 168 registers and the TMA-residual epilogue of the short-K layers then runs 20 % slower);
+// the MMA issuers wait for the landed patch directly.  XFORM = true: 384 threads, GroupNorm(+SiLU) in the operand path.
+template <bool BF16, bool XFORM>
+__global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * 128;
@@ -106,11 +109,11 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
 
   if (warp < 4) {
     // ===================================================================== epilogue
-    setmaxnreg_inc<232>();
+    if constexpr (XFORM) setmaxnreg_inc<232>();
     if (p.tma_store) epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
     else epilogue_direct<BF16>(p, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
   } else if (warp < 8) {
-    setmaxnreg_dec<72>();
+    if constexpr (XFORM) setmaxnreg_dec<72>();
     if (warp == 4) {
       // =================================================================== patch producer
       const bool leader = elect_one();
@@ -181,7 +184,11 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
           const bool trm = p.trace != nullptr && blockIdx.x == 0 && h == 0 && leader;
           const int mix = trm ? mma_n++ : 0;
           if (trm && mix < 60) p.trace[mix * 8 + 4] = clock64();
-          mbar_wait(&a_ready[slot], a_phase, 3);
+          if constexpr (XFORM) {
+            mbar_wait(&a_ready[slot], a_phase, 3);
+          } else {
+            for (int g = 0; g < p.TH + 2; ++g) mbar_wait(&a_full[slot * 4 + g], a_phase, 3);    // every patch row has landed
+          }
           tc_fence_after();
           if (trm && mix < 60) p.trace[mix * 8 + 5] = clock64();
           const uint32_t patch = smem_u32(smem + slot * p.a_slot_bytes);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if constexpr (XFORM) {
     // ===================================================================== operand transform (warps 8..11)
     setmaxnreg_dec<104>();
     const int tt = threadIdx.x - 256;                // 0..127
@@ -364,16 +371,22 @@ cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t s
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_patch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(igemm_patch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return e;
+    const void* fns[4] = {(const void*)igemm_patch_kernel<false, false>, (const void*)igemm_patch_kernel<false, true>,
+                          (const void*)igemm_patch_kernel<true, false>, (const void*)igemm_patch_kernel<true, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e != cudaSuccess) return e;
+    }
     attr_set[dev] = true;
   }
-  if (p.flags & IG_BF16)
-    igemm_patch_kernel<true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
-  else
-    igemm_patch_kernel<false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+  const bool xform = p.gn_ss != nullptr;
+  if (p.flags & IG_BF16) {
+    if (xform) igemm_patch_kernel<true, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+    else igemm_patch_kernel<true, false><<<grid, 256, kMaxSmem, stream>>>(p);
+  } else {
+    if (xform) igemm_patch_kernel<false, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+    else igemm_patch_kernel<false, false><<<grid, 256, kMaxSmem, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
