@@ -21,6 +21,7 @@ P = os.path.join(ROOT, "profiles")
 
 def cat(n):
     if "fattn" in n: return "fused attention (d=64)"
+    if n.endswith("conv_in") and "encoder" in n: return "convolutions (igemm)"
     if ".softmax" in n: return "softmax rows (VAE d=512 attention)"
     if n.endswith(".qk") or n.endswith(".pv") or "to_vT" in n or "to_qk" in n: return "attention GEMMs (igemm)"
     if (".norm1" in n and "transformer" in n) or ".norm3" in n: return "LayerNorm"
@@ -182,7 +183,9 @@ def main():
     parts.append(ncu_extract("prof_igemm.ncu-rep", tag, "igemm",
                              [(3, "conv3x3 128->128 @768x768 B=8 (patch-resident main loop)"),
                               (7, "conv3x3 256->256 @384x384 B=8 (tap-streaming main loop, BN=256)"),
-                              (11, "linear 320->2560 on 73728 tokens")]))
+                              (11, "linear 320->2560 on 73728 tokens"),
+                              (15, "K-packed stem: 1x1 GEMM 32(27)->128 on 8 x 768 x 768 pixels"),
+                              (16, "conv3x3 128->128 @768x768 B=8 with GroupNorm+SiLU in the operand path (GP_GN_FUSE=1)")]))
     parts.append(ncu_extract("prof_fattn.ncu-rep", tag, "fattn", [(1, "fused attention T=9216, 5 heads, d=64, B=8")]))
     open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n\n".join(p for p in parts if p) + "\n")
     print("\n\n".join(p for p in parts if p)[:3000])
