@@ -407,15 +407,14 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     GP_REQUIRE(p.TW == 128 && p.TH == p.MT, name + ": patch tile");
     p.patch = 1;
     p.kc_count = ceil_div(s0.C, 64);
-    // one TMA box per image row of the patch (igemm_patch.cu): box (64 channels, 130 pixels, 1 row, 1 image)
     check_cuda(make_tmap_a(&p.tmPatch, ptr(s0), s0.C, W, H, N, s0.C, (long long)W * s0.C, (long long)H * W * s0.C,
-                           p.TW + 2, 1, bf16_), name + ": tmap patch");
+                           p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch");
     p.tmPatch2 = p.tmPatch;
     if (!a.sc.empty()) {
       const T4& x = a.sc[0];
       p.kc_sc = ceil_div(x.C, 64);
       check_cuda(make_tmap_a(&p.tmPatch2, ptr(x), x.C, W, H, N, x.C, (long long)W * x.C, (long long)H * W * x.C,
-                             p.TW + 2, 1, bf16_), name + ": tmap patch (shortcut)");
+                             p.TW + 2, p.TH + 2, bf16_), name + ": tmap patch (shortcut)");
     }
     if (gn_fused) {
       p.gn_ss = gn_ss;

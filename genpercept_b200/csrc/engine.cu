@@ -1852,12 +1852,26 @@ gp_status gp_bench_conv(int dtype, int N, int H, int W, int Cin, int Cout, int k
     te.e.dev_allocs.push_back(x);
     te.e.dev_allocs.push_back(y);
     GP_CUDA(cudaMemset(x, 0, (size_t)N * H * W * Cin * 2));
-    Builder b(te.e.bf16, false, nullptr);
+    // a scratch arena for the epilogue statistics (GP_BENCH_STATS=1); externals are addressed relative to it
+    void* scratch = nullptr;
+    GP_CUDA(cudaMalloc(&scratch, (size_t)N * 160 * Cout * 2 * sizeof(float) + (1 << 20)));
+    te.e.dev_allocs.push_back(scratch);
+    Builder b(te.e.bf16, false, reinterpret_cast<uint8_t*>(scratch));
     ConvArgs c;
     c.srcs = {b.external(x, N, H, W, Cin)};
     c.ks = ks; c.mode = mode;
     c.w = (mode == 3) ? &te.e.conv_up_w("t") : &te.e.conv_w("t", {Cin});
     c.out = b.external(y, N, Ho, Wo, Cout);
+    if (std::getenv("GP_BENCH_STATS")) c.want_stats = true;      // epilogue experiments: also emit the GroupNorm partial sums
+    void* res = nullptr;
+    T4 rest;
+    if (std::getenv("GP_BENCH_RES")) {              // ... and / or add a residual of the output's shape
+      GP_CUDA(cudaMalloc(&res, (size_t)N * Ho * Wo * Cout * 2));
+      GP_CUDA(cudaMemset(res, 0, (size_t)N * Ho * Wo * Cout * 2));
+      te.e.dev_allocs.push_back(res);
+      rest = b.external(res, N, Ho, Wo, Cout);
+      c.res1 = &rest;
+    }
     b.conv("bench", c);
     cudaEvent_t e0, e1;
     GP_CUDA(cudaEventCreate(&e0));

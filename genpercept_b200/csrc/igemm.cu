@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
-  float* sacc = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][Cout][2], only with p.stats
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
+  float* sacc = sbias + kBiasSlots;   // [4 epilogue warps][Cout][2], only with p.stats
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -168,9 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp < 4 && p.tma_store) {
-    epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    epilogue_staged<BF16>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
   } else if (warp < 4) {
-    epilogue_direct<BF16>(p, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    epilogue_direct<BF16>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -274,14 +275,14 @@ const char* igemm_finalize(IgemmParams* p) {
     return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
   if (p->tma_store && (p->flags & IG_GEGLU) && ((p->Cout % 128) || (p->BN % 128))) return "staged GEGLU needs Cout, BN % 128 == 0";
   if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
-  int st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? (p->out_lo ? 8 : 4) * 4096 : 0)) / stage_bytes;
+  int st = (kMaxSmem - 3072 - stats_bytes - (p->tma_store ? (p->out_lo ? 8 : 4) * 4096 : 0)) / stage_bytes;
   if (p->patch) {
     if (p->TW != 128 || p->TH != p->MT || p->Z0 != 1 || p->Z1 < 1 || p->nseg[0] != 9 + (p->kc_sc > 0 ? 1 : 0) || p->kc_count < 1 ||
         p->nkb[0] != 9 * p->kc_count + p->kc_sc || p->npass != 1 || p->gridW % 128 || p->gridH % p->TH)
       return "patch mode needs TW = 128, TH = MT, full tiles and a single-source 3x3 tap table (+ shortcut chunks)";
     if (p->gn_ss && p->gn_C != p->kc_count * 64) return "patch mode: GroupNorm channels must equal the source's";
-    p->a_slot_bytes = 136 * (p->TH + 2) * 128;      // igemm_patch.cu kPP: 130 pixels per patch row at a 136-row pitch
-    st = (kMaxSmem - 2048 - stats_bytes - (p->tma_store ? 4 * 4096 : 0) - 2 * p->a_slot_bytes) / (p->BN * 128);
+    p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
+    st = (kMaxSmem - 3072 - stats_bytes - (p->tma_store ? 4 * 4096 : 0) - 2 * p->a_slot_bytes) / (p->BN * 128);
     if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
       const int v = atoi(env);
       if (v >= 2 && v < st) st = v;

@@ -103,11 +103,32 @@ __device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// The bias of the CTA's current N tile lives in shared memory (kBiasSlots floats, zero beyond Cout): every 32-column piece
+// of the epilogue used to fetch it with eight dependent 16-byte global loads — with almost all of L1 configured as shared
+// memory those miss to L2 (~600 cycles), in front of every piece (ncu r2: the K = 1 stem GEMM, nothing but epilogue, ran
+// with the epilogue warps issuing 22 % of the time and no unit above 25 %).
+constexpr int kBiasSlots = 288;
+__device__ __forceinline__ void load_bias_tile(const IgemmParams& p, float* sbias, int n_base, int etid) {
+  epi_sync();                                  // nobody still reads the previous tile's values
+  for (int i = etid; i < kBiasSlots; i += 128) {
+    const int n = n_base + i;
+    sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+  }
+  epi_sync();
+}
+__device__ __forceinline__ void bias32(const float* sbias, int c, float (&bz)[32]) {
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + q);
+    bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
+  }
+}
+
 // Staged epilogue (shared by the tap-streaming and the patch-resident main loops): TMEM -> registers
 // (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile -> one TMA store per
 // (warp, 64-channel group), plus the GroupNorm partial sums read back column-wise from the tile.
 template <bool BF16>
-__device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, uint64_t* tfull_bar,
+__device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, float* sbias, uint64_t* tfull_bar,
                                                 uint64_t* tempty_bar, uint64_t* res_bar, uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue, staged + TMA store
   // TMEM -> registers (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile ->
@@ -128,6 +149,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   const bool do_stats = p.stats != nullptr;
   const int etid = threadIdx.x;
   int cur_img = -1;
+  int cur_nt = -1;
   auto flush_stats = [&](int img) {
     epi_sync();
     float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
@@ -147,6 +169,10 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
     const int cls = p.cls_from_z0 ? t.z0 : 0;
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
+    if (t.n_tile != cur_nt) {
+      load_bias_tile(p, sbias, n_base, etid);
+      cur_nt = t.n_tile;
+    }
     // The residual boxes of this CTA's NEXT tile are pulled into L2 now, a whole tile period before their TMA loads:
     // those loads sit serially in front of every 32 x 64 piece of the epilogue, and with DRAM latency (1.5 us under
     // load) four of them per warp outlast the main loop of the short-K (Cout = 128) layers (r2: residual convs 20-30 %
@@ -189,15 +215,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           for (int sub = 0; sub < 4; ++sub) {
             const int ns = n0 + sub * 32;
             float bz[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) bz[q] = 0.f;
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int q = 0; q < 32; q += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
-                bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
-              }
-            }
+            bias32(sbias, ns - n_base, bz);
             if (!waited) {
               mbar_wait(&tfull_bar[acc], acc_phase, 4);
               tc_fence_after();
@@ -252,15 +270,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           const int ns = n0 + sub * 32;
           const long long off = pix_off + ns;
           float bz[32];
-#pragma unroll
-          for (int q = 0; q < 32; ++q) bz[q] = 0.f;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ns + q));
-              bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
-            }
-          }
+          bias32(sbias, ns - n_base, bz);
           uint4 r1[4], r2[4];
           const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
           if (p.res_tma) {
@@ -373,7 +383,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
 // Direct epilogue: TMEM -> registers (bias / residuals / ReLU / affine clamp / GEGLU) -> global stores straight from
 // the registers: fp32 NCHW maps, odd channel counts, GEGLU, the high-precision (hi, lo) layout.
 template <bool BF16>
-__device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sacc, uint64_t* tfull_bar, uint64_t* tempty_bar,
+__device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sacc, float* sbias, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                 uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue
   const int wq = warp;                     // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
@@ -386,6 +396,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
   const bool do_stats = false;               // statistics are produced by the staged (TMA store) epilogue only
   const int etid = threadIdx.x;              // 0..127 among the epilogue threads
   int cur_img = -1;
+  int cur_nt = -1;
   // sum the four warp-private accumulators in a fixed order, publish this CTA's slot, reset
   auto flush_stats = [&](int img) {
     epi_sync();
@@ -406,6 +417,10 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
     const int cls = p.cls_from_z0 ? t.z0 : 0;
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
+    if (t.n_tile != cur_nt) {
+      load_bias_tile(p, sbias, n_base, etid);
+      cur_nt = t.n_tile;
+    }
     if (do_stats) {
       const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
       if (img != cur_img) {
@@ -431,20 +446,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
         const bool vec = !f32out && live && (nvalid == ncols) && ((off & 7) == 0);
         // operands that do not depend on the accumulator are fetched BEFORE waiting on it
         float bz[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) bz[q] = 0.f;
-        if (live && p.bias != nullptr) {
-          if (nvalid == 32) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + q));
-              bz[q] = b4.x; bz[q + 1] = b4.y; bz[q + 2] = b4.z; bz[q + 3] = b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) if (q < nvalid) bz[q] = __ldg(p.bias + n0 + q);
-          }
-        }
+        bias32(sbias, c0, bz);
         uint4 r1[4], r2[4];
         const bool has1 = vec && p.res1 != nullptr, has2 = vec && p.res2 != nullptr;
         if (has1) {

@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kPatchThreads = 384;
 constexpr int kPW = kBM + 2;      // patch width in pixels (TW = 128)
-constexpr int kPP = 136;          // patch row pitch in pixels: every image row of the patch starts on a 1024-byte swizzle atom
+constexpr int kPP = kPW;          // patch row pitch in pixels (one TMA box per patch: rows are contiguous)
 
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
-  float* sacc = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
+  float* sacc = sbias + kBiasSlots;
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
   if (warp < 4) {
     // ===================================================================== epilogue
     if constexpr (XFORM) setmaxnreg_inc<232>();
-    if (p.tma_store) epilogue_staged<BF16>(p, stg_base, sacc, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
-    else epilogue_direct<BF16>(p, sacc, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    if (p.tma_store) epilogue_staged<BF16>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    else epilogue_direct<BF16>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   } else if (warp < 8) {
     if constexpr (XFORM) setmaxnreg_dec<72>();
     if (warp == 4) {
@@ -126,13 +127,12 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
           const bool main = kc < p.kc_count;
           mbar_wait(&a_empty[slot], phase ^ 1, 1);
           if (leader) {
-            // one box per image row of the patch, each on its own barrier: the transform starts on the first row while
-            // the others are still in flight
-            for (int g = 0; g < p.TH + 2; ++g) {
-              mbar_expect_tx(&a_full[slot * 4 + g], (uint32_t)(kPW * 128));
-              tma_load_4d(smem + slot * p.a_slot_bytes + g * (kPP * 128), main ? &p.tmPatch : &p.tmPatch2, &a_full[slot * 4 + g],
-                          (main ? kc : kc - p.kc_count) * kBK, x0, y0 + g, t.z1);
-            }
+            // ONE box per patch.  (One box per patch row on its own barrier — so that the transform could start on the
+            // first row — was tried in round 2: 902 us against 728 us for the plain 128->128 layer, tensor pipe 78 % vs
+            // 92 %, +32 % DRAM reads: profiles/r2_igemm_ncu_set_full.txt.)
+            mbar_expect_tx(&a_full[slot * 4], (uint32_t)((p.TH + 2) * kPW * 128));
+            tma_load_4d(smem + slot * p.a_slot_bytes, main ? &p.tmPatch : &p.tmPatch2, &a_full[slot * 4],
+                        (main ? kc : kc - p.kc_count) * kBK, x0, y0, t.z1);
           }
           __syncwarp();
           if (++slot == 2) { slot = 0; phase ^= 1; }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
           if constexpr (XFORM) {
             mbar_wait(&a_ready[slot], a_phase, 3);
           } else {
-            for (int g = 0; g < p.TH + 2; ++g) mbar_wait(&a_full[slot * 4 + g], a_phase, 3);    // every patch row has landed
+            mbar_wait(&a_full[slot * 4], a_phase, 3);                                            // the patch has landed
           }
           tc_fence_after();
           if (trm && mix < 60) p.trace[mix * 8 + 5] = clock64();
@@ -266,11 +266,10 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
         const bool trx = p.trace != nullptr && blockIdx.x == 0 && tt == 0;
         const int tix = trx ? trace_n++ : 0;
         if (trx && tix < 60) p.trace[tix * 8 + 0] = clock64();
-        int landed = 0;                              // patch rows whose barrier this thread has passed
+        mbar_wait(&a_full[slot * 4], phase, 8);
+        if (trx && tix < 60) p.trace[tix * 8 + 1] = clock64();
         if (!xf) {
-          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
-        } else if (p.gn_mode & 2) {                  // experiment: one row per iteration after the whole patch has landed
-          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
+        } else if (p.gn_mode & 2) {                  // experiment: one row per iteration
           const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
           int py = 0, px = rbase;
           for (int r = rbase; r < prows; r += 16) {
@@ -297,20 +296,11 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
           }
           fence_proxy_async_shared();
         } else {
-          if (p.gn_mode & 1)                         // experiment: start only when the whole patch has landed
-            for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);
           const uint32_t base = smem_u32(smem + slot * p.a_slot_bytes) + cpos * 16;
           int py = 0, px = rbase;                    // rbase < 16 < kPW
           for (int r = rbase; r < prows; r += 64) {  // four rows in flight per thread
             uint32_t w[4][4];
             bool ok[4];
-            {
-              const int last = min(r + 48, prows - 1) / kPP;      // deepest patch row this group of four touches
-              for (; landed <= last; ++landed) {
-                mbar_wait(&a_full[slot * 4 + landed], phase, 8);
-                if (trx && tix < 60 && landed == 0) p.trace[tix * 8 + 1] = clock64();
-              }
-            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int rr = r + 16 * u;
@@ -339,7 +329,6 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
                            "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
             }
           }
-          for (; landed < p.TH + 2; ++landed) mbar_wait(&a_full[slot * 4 + landed], phase, 8);   // keep the phases in step
           fence_proxy_async_shared();                // generic-proxy writes -> visible to the tensor core's reads
         }
         if (trx && tix < 60) p.trace[tix * 8 + 2] = clock64();
