@@ -26,20 +26,23 @@ namespace gp {
 
 namespace {
 
+constexpr int kEpiWarps = 8;                         // epilogue warps 0..7; the single-thread roles are warps 8..11
+constexpr int kTapThreads = (kEpiWarps + 4) * 32;    // 384
+
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = kABytes * p.MT;
   const int stage_bytes = a_bytes + p.BN * 128;
   const int stages = p.stages;
-  uint8_t* stg_base = smem + stages * stage_bytes;                     // 4 x 4 KiB staging tiles (tma_store only)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? (p.out_lo ? 8 : 4) * 4096 : 0));
+  uint8_t* stg_base = smem + stages * stage_bytes;                     // one 4 KiB staging tile per epilogue warp (tma_store only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? (p.out_lo ? 2 : 1) * kEpiWarps * 4096 : 0));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  uint64_t* res_bar = tempty_bar + 2;                                  // [epilogue warps] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
   float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
   float* sacc = sbias + kBiasSlots;   // [4 epilogue warps][Cout][2], only with p.stats
 
@@ -55,12 +58,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], p.MT);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiWarps * 32);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kEpiWarps + 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   // Single-thread roles run warp-uniform (every lane walks the loop and waits on the barriers) and one
   // elected lane issues: the TMA coordinates / UMMA descriptors then stay in uniform registers.
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     // ===================================================================== TMA producer A
     const bool leader = elect_one();
     int stage = 0;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
       }
     }
-  } else if (warp == 7) {
+  } else if (warp == kEpiWarps + 3) {
     // ===================================================================== TMA producer B
     const bool leader = elect_one();
     int stage = 0;
@@ -125,14 +128,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
       }
     }
-  } else if (warp == 5 || (warp == 6 && p.MT == 2)) {
+  } else if (warp == kEpiWarps + 1 || (warp == kEpiWarps + 2 && p.MT == 2)) {
     const bool leader = elect_one();
     // ===================================================================== MMA issuer(s)
     // With two accumulator tiles (MT = 2, BN <= 128) each tile gets its own issuing thread: a single
     // thread cannot issue one 64-cycle 128x128x16 MMA every 64 cycles once descriptor arithmetic and
     // barrier polls are added (ncu r1h: tensor pipe 57 % busy, issuer never blocked on a barrier).
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
-    const int h_lo = warp - 5, h_hi = (p.MT == 2) ? warp - 4 : 1;
+    const int h_lo = warp - (kEpiWarps + 1), h_hi = (p.MT == 2) ? warp - kEpiWarps : 1;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -168,15 +171,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp < 4 && p.tma_store) {
-    epilogue_staged<BF16>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
-  } else if (warp < 4) {
-    epilogue_direct<BF16>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  } else if (warp < kEpiWarps && p.tma_store) {
+    epilogue_staged<BF16, kEpiWarps>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+  } else if (warp < kEpiWarps) {
+    epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) {
+  if (warp == kEpiWarps + 2) {
     __syncwarp();          // reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -275,14 +278,17 @@ const char* igemm_finalize(IgemmParams* p) {
     return "staged epilogue needs Cout % 64 == 0, BN % 64 == 0, plain 16-bit NHWC output";
   if (p->tma_store && (p->flags & IG_GEGLU) && ((p->Cout % 128) || (p->BN % 128))) return "staged GEGLU needs Cout, BN % 128 == 0";
   if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
-  int st = (kMaxSmem - 3072 - stats_bytes - (p->tma_store ? (p->out_lo ? 8 : 4) * 4096 : 0)) / stage_bytes;
+  // staging: one 4 KiB tile per epilogue warp (8; 4 in the patch kernel's GroupNorm-transform build), x2 for the (hi, lo) layout
+  const int epi_warps = (p->patch && p->gn_ss) ? 4 : 8;
+  const int staging = p->tma_store ? epi_warps * 4096 * (p->out_lo ? 2 : 1) : 0;
+  int st = (kMaxSmem - 3072 - stats_bytes - staging) / stage_bytes;
   if (p->patch) {
     if (p->TW != 128 || p->TH != p->MT || p->Z0 != 1 || p->Z1 < 1 || p->nseg[0] != 9 + (p->kc_sc > 0 ? 1 : 0) || p->kc_count < 1 ||
         p->nkb[0] != 9 * p->kc_count + p->kc_sc || p->npass != 1 || p->gridW % 128 || p->gridH % p->TH)
       return "patch mode needs TW = 128, TH = MT, full tiles and a single-source 3x3 tap table (+ shortcut chunks)";
     if (p->gn_ss && p->gn_C != p->kc_count * 64) return "patch mode: GroupNorm channels must equal the source's";
     p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
-    st = (kMaxSmem - 3072 - stats_bytes - (p->tma_store ? 4 * 4096 : 0) - 2 * p->a_slot_bytes) / (p->BN * 128);
+    st = (kMaxSmem - 3072 - stats_bytes - staging - 2 * p->a_slot_bytes) / (p->BN * 128);
     if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
       const int v = atoi(env);
       if (v >= 2 && v < st) st = v;
@@ -330,9 +336,9 @@ cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
   const size_t smem = kMaxSmem;
   if (p.patch) return igemm_patch_launch(p, grid, stream);
   if (p.flags & IG_BF16) {
-    igemm_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    igemm_kernel<true><<<grid, kTapThreads, smem, stream>>>(p);
   } else {
-    igemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+    igemm_kernel<false><<<grid, kTapThreads, smem, stream>>>(p);
   }
   return cudaGetLastError();
 }

@@ -99,8 +99,12 @@ __device__ __forceinline__ float gelu_erf(float g) {
   return g * (g >= 0.f ? 1.f - q : q);
 }
 
-__device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+// NW epilogue warps (4 or 8).  With 8, warps w and w + 4 read the same TMEM lane quadrant (lanes 32 * (w % 4) ...) and split the
+// tile's 64-channel groups between them: one epilogue warp per sub-partition is stalled ~78 % of the time (TMEM / shared
+// memory latency, instruction fetch: ncu r2, the K = 1 stem GEMM), a second one fills those slots.
+template <int NW>
+__device__ __forceinline__ void epi_sync() {   // the epilogue threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
 }
 
 // The bias of the CTA's current N tile lives in shared memory (kBiasSlots floats, zero beyond Cout): every 32-column piece
@@ -108,13 +112,14 @@ __device__ __forceinline__ void epi_sync() {   // the 128 epilogue threads only
 // memory those miss to L2 (~600 cycles), in front of every piece (ncu r2: the K = 1 stem GEMM, nothing but epilogue, ran
 // with the epilogue warps issuing 22 % of the time and no unit above 25 %).
 constexpr int kBiasSlots = 288;
+template <int NW>
 __device__ __forceinline__ void load_bias_tile(const IgemmParams& p, float* sbias, int n_base, int etid) {
-  epi_sync();                                  // nobody still reads the previous tile's values
-  for (int i = etid; i < kBiasSlots; i += 128) {
+  epi_sync<NW>();                              // nobody still reads the previous tile's values
+  for (int i = etid; i < kBiasSlots; i += NW * 32) {
     const int n = n_base + i;
     sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
   }
-  epi_sync();
+  epi_sync<NW>();
 }
 __device__ __forceinline__ void bias32(const float* sbias, int c, float (&bz)[32]) {
 #pragma unroll
@@ -127,7 +132,7 @@ __device__ __forceinline__ void bias32(const float* sbias, int c, float (&bz)[32
 // Staged epilogue (shared by the tap-streaming and the patch-resident main loops): TMEM -> registers
 // (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile -> one TMA store per
 // (warp, 64-channel group), plus the GroupNorm partial sums read back column-wise from the tile.
-template <bool BF16>
+template <bool BF16, int NW>
 __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, float* sbias, uint64_t* tfull_bar,
                                                 uint64_t* tempty_bar, uint64_t* res_bar, uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue, staged + TMA store
@@ -135,12 +140,18 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   // one TMA store per (warp, 64-channel group): full-line writes instead of 16-byte pieces at a
   // 2C-byte stride, and image-edge clipping for free.  GroupNorm partial sums are read back
   // column-wise from the staged tile (conflict-free), in a fixed order.
-  const int wq = warp;                       // epilogue warps are warps 0..3 (== warp % 4 -> TMEM lanes [32*wq, +32))
-  uint8_t* stg = stg_base + wq * 4096;
+  const int wq = warp & 3;                   // epilogue warps are warps 0..NW-1; warp % 4 -> TMEM lanes [32*wq, +32)
+  const int half = warp >> 2;                // NW == 8: which of the tile's 64-channel groups this warp takes (parity)
+  uint8_t* stg = stg_base + warp * 4096;
   const uint32_t stg_addr = smem_u32(stg);
   const uint32_t my_row = stg_addr + lane * 128;
-  const bool split = p.out_lo != 0;          // high-precision mode: a second staged tile (+16 KiB) takes the lo plane
-  const uint32_t my_row_lo = my_row + 4 * 4096;
+  const bool split = p.out_lo != 0;          // high-precision mode: a second staged tile (+NW * 4 KiB) takes the lo plane
+  const uint32_t my_row_lo = my_row + NW * 4096;
+  // 64-channel groups (128 GEMM columns with GEGLU) of the N tile go to the two halves by parity; a tile with one group only
+  // is done by half 0 (statistics: the halves then never accumulate the same channel into sacc[wq])
+  const int gshift = (p.flags & IG_GEGLU) ? 7 : 6;
+  const bool two_groups = NW == 8 && (p.BN >> gshift) >= 2;
+  auto mine = [&](int c0) { return NW == 4 || (two_groups ? ((c0 >> gshift) & 1) == half : half == 0); };
   const int sw = lane & 7;
   int acc = 0;
   uint32_t acc_phase = 0, res_phase = 0;
@@ -151,18 +162,18 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   int cur_img = -1;
   int cur_nt = -1;
   auto flush_stats = [&](int img) {
-    epi_sync();
+    epi_sync<NW>();
     float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
-    for (int i = etid; i < 2 * p.Cout; i += 128) {
+    for (int i = etid; i < 2 * p.Cout; i += NW * 32) {
       const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
       dst[i] = tot;
       sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
     }
-    epi_sync();
+    epi_sync<NW>();
   };
   if (do_stats) {
-    for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
-    epi_sync();
+    for (int i = etid; i < 8 * p.Cout; i += NW * 32) sacc[i] = 0.f;
+    epi_sync<NW>();
   }
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
@@ -170,7 +181,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
     if (t.n_tile != cur_nt) {
-      load_bias_tile(p, sbias, n_base, etid);
+      load_bias_tile<NW>(p, sbias, n_base, etid);
       cur_nt = t.n_tile;
     }
     // The residual boxes of this CTA's NEXT tile are pulled into L2 now, a whole tile period before their TMA loads:
@@ -184,7 +195,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
         const int r0 = h * 128 + wq * 32;
         const int psx = tn.tx * p.TW + (r0 & (p.TW - 1)), psy = tn.ty * p.TH + (r0 >> p.tw_shift);
         for (int c0 = 0; c0 < p.BN && tn.n_tile * p.BN + c0 < p.Cout; c0 += 64)
-          tma_prefetch_l2_4d(&p.tmRes[ncls], tn.n_tile * p.BN + c0, psx, psy, tn.z1);
+          if (mine(c0)) tma_prefetch_l2_4d(&p.tmRes[ncls], tn.n_tile * p.BN + c0, psx, psy, tn.z1);
       }
     }
     if (do_stats) {
@@ -207,6 +218,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
       for (int c0 = 0; c0 < p.BN; c0 += 64) {
         const int n0 = n_base + c0;
         if (n0 >= p.Cout) break;
+        if (!mine(c0)) continue;
         if (geglu) {   // 128 GEMM columns = 4 x [16 values | 16 gates] -> 64 outputs = one staged 128-byte row
           if (c0 & 64) continue;
           if (lane == 0) tma_store_wait_read0();
@@ -252,10 +264,10 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
         uint4 rt[8];                                          // this thread's residual row (64 channels), res_tma only
         if (p.res_tma) {
           if (lane == 0) {
-            mbar_expect_tx(&res_bar[wq], 4096);
-            tma_load_4d(stg, &p.tmRes[cls], &res_bar[wq], n0, sx, sy, t.z1);
+            mbar_expect_tx(&res_bar[warp], 4096);
+            tma_load_4d(stg, &p.tmRes[cls], &res_bar[warp], n0, sx, sy, t.z1);
           }
-          mbar_wait(&res_bar[wq], res_phase, 7);
+          mbar_wait(&res_bar[warp], res_phase, 7);
           res_phase ^= 1;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -347,7 +359,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&p.tmOut[cls], stg_addr, n0, sx, sy, t.z1);
-          if (split) tma_store_4d(&p.tmOutLo[cls], stg_addr + 4 * 4096, n0, sx, sy, t.z1);
+          if (split) tma_store_4d(&p.tmOutLo[cls], stg_addr + NW * 4096, n0, sx, sy, t.z1);
           tma_store_commit();
         }
         if (do_stats) {
@@ -382,11 +394,13 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
 
 // Direct epilogue: TMEM -> registers (bias / residuals / ReLU / affine clamp / GEGLU) -> global stores straight from
 // the registers: fp32 NCHW maps, odd channel counts, GEGLU, the high-precision (hi, lo) layout.
-template <bool BF16>
+template <bool BF16, int NW>
 __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sacc, float* sbias, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                 uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue
-  const int wq = warp;                     // == warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
+  const int wq = warp & 3;                 // warp % 4 -> TMEM lanes [32*wq, 32*wq+32)
+  const int half = warp >> 2;              // NW == 8: the tile's 32-column chunks go to the two halves by parity
+  const bool two_chunks = NW == 8 && p.BN > 32;
   int acc = 0;
   uint32_t acc_phase = 0;
   const bool f32out = (p.flags & IG_OUT_F32_NCHW) != 0;
@@ -399,18 +413,18 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
   int cur_nt = -1;
   // sum the four warp-private accumulators in a fixed order, publish this CTA's slot, reset
   auto flush_stats = [&](int img) {
-    epi_sync();
+    epi_sync<NW>();
     float* dst = p.stats + ((long long)img * p.stats_slots + blockIdx.x) * p.Cout * 2;
-    for (int i = etid; i < 2 * p.Cout; i += 128) {
+    for (int i = etid; i < 2 * p.Cout; i += NW * 32) {
       const float tot = (sacc[i] + sacc[2 * p.Cout + i]) + (sacc[4 * p.Cout + i] + sacc[6 * p.Cout + i]);
       dst[i] = tot;
       sacc[i] = 0.f; sacc[2 * p.Cout + i] = 0.f; sacc[4 * p.Cout + i] = 0.f; sacc[6 * p.Cout + i] = 0.f;
     }
-    epi_sync();
+    epi_sync<NW>();
   };
   if (do_stats) {
-    for (int i = etid; i < 8 * p.Cout; i += 128) sacc[i] = 0.f;
-    epi_sync();
+    for (int i = etid; i < 8 * p.Cout; i += NW * 32) sacc[i] = 0.f;
+    epi_sync<NW>();
   }
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
@@ -418,7 +432,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
     if (t.n_tile != cur_nt) {
-      load_bias_tile(p, sbias, n_base, etid);
+      load_bias_tile<NW>(p, sbias, n_base, etid);
       cur_nt = t.n_tile;
     }
     if (do_stats) {
@@ -438,6 +452,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
                                 (long long)ox * p.out_pix_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        if (NW == 8 && (two_chunks ? ((c0 >> 5) & 1) != half : half != 0)) continue;
         const int ncols = (p.BN - c0 >= 32) ? 32 : 16;
         const int n0 = n_base + c0;
         const int nvalid = min(ncols, p.Cout - n0);

@@ -64,22 +64,24 @@ __device__ __forceinline__ uint32_t silu_pair_f16(float ha, float hb) {     // i
 // build caps every thread at 168 registers and the TMA-residual epilogue of the short-K layers then runs 20 % slower);
 // the MMA issuers wait for the landed patch directly.  XFORM = true: 384 threads, GroupNorm(+SiLU) in the operand path.
 template <bool BF16, bool XFORM>
-__global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
+  // XFORM = false: warps 0..7 epilogue, 8..11 roles.  XFORM = true: warps 0..3 epilogue, 4..7 roles, 8..11 transform.
+  constexpr int NE = XFORM ? 4 : 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * 128;
   const int stages = p.stages;                       // depth of the weight ring
   uint8_t* sB = smem + 2 * p.a_slot_bytes;
   uint8_t* stg_base = sB + stages * b_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? 4 * 4096 : 0));   // [slot][patch row]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? NE * 4096 : 0));   // [slot][4]: only [slot][0] is used
   uint64_t* a_ready = a_full + 8;
   uint64_t* a_empty = a_ready + 2;
   uint64_t* b_full = a_empty + 2;
   uint64_t* b_empty = b_full + stages;
   uint64_t* tfull_bar = b_empty + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;                                  // [4 epilogue warps] residual tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  uint64_t* res_bar = tempty_bar + 2;                                  // [epilogue warps] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
   float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
   float* sacc = sbias + kBiasSlots;
 
@@ -98,24 +100,25 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
       mbar_init(&a_empty[i], p.MT);                  // one tcgen05.commit per MMA issuer
     }
     for (int i = 0; i < stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], 128); }
-    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], NE * 32); }
+    for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc(tmem_slot, kTmemCols);
+  const int rw = warp - NE;                          // role index: 0 patch producer, 1 / 2 MMA issuers, 3 weight producer
+  if (rw == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < NE) {
     // ===================================================================== epilogue
     if constexpr (XFORM) setmaxnreg_inc<232>();
-    if (p.tma_store) epilogue_staged<BF16>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
-    else epilogue_direct<BF16>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
-  } else if (warp < 8) {
+    if (p.tma_store) epilogue_staged<BF16, NE>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    else epilogue_direct<BF16, NE>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  } else if (rw < 4) {
     if constexpr (XFORM) setmaxnreg_dec<72>();
-    if (warp == 4) {
+    if (rw == 0) {
       // =================================================================== patch producer
       const bool leader = elect_one();
       int slot = 0;
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
           if (++slot == 2) { slot = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 7) {
+    } else if (rw == 3) {
       // =================================================================== weight producer
       const bool leader = elect_one();
       int stage = 0;
@@ -162,11 +165,11 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
           }
         }
       }
-    } else if (warp - 5 < p.MT) {
+    } else if (rw - 1 < p.MT) {
       // =================================================================== MMA issuers (one per image row h)
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc_f16(kBM, p.BN, BF16 ? 1 : 0);
-      const int h = warp - 5;
+      const int h = rw - 1;
       int slot = 0, stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       int acc = 0;
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(XFORM ? kPatchThreads : 256, 1) igemm_patch_ke
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) {
+  if (rw == 2) {
     __syncwarp();          // reconverge before the .aligned dealloc
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -371,10 +374,10 @@ cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t s
   const bool xform = p.gn_ss != nullptr;
   if (p.flags & IG_BF16) {
     if (xform) igemm_patch_kernel<true, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
-    else igemm_patch_kernel<true, false><<<grid, 256, kMaxSmem, stream>>>(p);
+    else igemm_patch_kernel<true, false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
   } else {
     if (xform) igemm_patch_kernel<false, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
-    else igemm_patch_kernel<false, false><<<grid, 256, kMaxSmem, stream>>>(p);
+    else igemm_patch_kernel<false, false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
   }
   return cudaGetLastError();
 }

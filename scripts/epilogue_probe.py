@@ -15,7 +15,6 @@ VARIANTS = {"plain": {}, "stats": {"GP_BENCH_STATS": "1"}, "residual": {"GP_BENC
             "residual, per-thread loads": {"GP_BENCH_RES": "1", "GP_NO_RES_TMA": "1"}, "direct epilogue": {"GP_DIRECT_EPILOGUE": "1"}}
 for sname, shape in SHAPES.items():
     for vname, env in VARIANTS.items():
-        code = CODE % (repr(shape), "%s", "%s")
         code = ("import sys, torch; sys.path.insert(0, %r); from genpercept_b200 import engine as E; us, fl = E.bench_conv(torch.float16, *%r, iters=20); "
                 "print('%-30s %-28s %%7.0f us  %%6.0f TFLOP/s' %% (us, fl / us / 1e6))" % (ROOT, shape, sname, vname))
         p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
