@@ -1,18 +1,20 @@
 // tcgen05 implicit-GEMM kernel (see igemm.h for the operand model).
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over a static round-robin tile list).  The single-thread
-// producer / issuer roles sit in the HIGHEST warp ids (4..7): the SM sub-partition arbiter favours higher warp
-// ids, and an issuer starved by the epilogue warp of its sub-partition stalls the tensor pipe (fattn trace, r1h).
+// Warp roles (384 threads, 1 CTA / SM, persistent over a static round-robin tile list).  The single-thread
+// producer / issuer roles sit in the HIGHEST warp ids (8..11): the SM sub-partition arbiter favours higher warp
+// ids, and an issuer starved by the epilogue warps of its sub-partition stalls the tensor pipe (fattn trace, r1h).
 // Each single-thread role is executed by its WHOLE warp (every lane walks the loop and waits on the barriers) and
 // one elect.sync lane issues: coordinates and descriptors stay in uniform registers (back-to-back UTCHMMA).
-//   warp 4        : TMA producer A (activation box per 64-channel K block, `stages`-deep ring)
-//   warp 7        : TMA producer B (weight box per K block) — its own warp: one thread issuing
-//                   both boxes plus the barrier traffic could not keep up with BN=128 tiles
-//                   (ncu r1a: tensor pipe 45 % active on the 128->128 convs, DRAM/L2 not saturated)
-//   warp 5 (and 6): MMA issuer(s), one per accumulator tile (4 tcgen05.mma 128xBNx16 per K block; commit frees the slot)
-//   warp 6        : TMEM allocator (512 columns = 2 accumulator buffers x MT tiles)
-//   warps 0..3    : epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias / TMA-loaded residual / act -> staged tile
-//                   -> TMA store, GroupNorm partial sums from the staged tile)
+//   warp 8         : TMA producer A (activation box per 64-channel K block, `stages`-deep ring)
+//   warp 11        : TMA producer B (weight box per K block) — its own warp: one thread issuing
+//                    both boxes plus the barrier traffic could not keep up with BN=128 tiles
+//                    (ncu r1a: tensor pipe 45 % active on the 128->128 convs, DRAM/L2 not saturated)
+//   warp 9 (and 10): MMA issuer(s), one per accumulator tile (4 tcgen05.mma 128xBNx16 per K block; commit frees the slot)
+//   warp 10        : TMEM allocator (512 columns = 2 accumulator buffers x MT tiles)
+//   warps 0..7     : epilogue, two per sub-partition: warps w and w + 4 read the same TMEM lane quadrant and split the
+//                    tile's 64-channel groups (tcgen05.ld 32 lanes x 32 columns -> bias (from shared memory) / TMA-loaded
+//                    residual / act -> staged tile -> TMA store, GroupNorm partial sums from the staged tile).  One
+//                    epilogue warp per sub-partition was stalled 78 % of the time (ncu r2, the K = 1 stem GEMM).
 // MT = 2 (a 256-pixel M tile per CTA, two accumulators sharing every weight box) when BN <= 128:
 // halves the weight traffic and the per-byte barrier / TMA issue cost of the narrow-N layers.
 #include "igemm.h"

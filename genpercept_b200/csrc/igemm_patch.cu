@@ -19,11 +19,11 @@
 // Extra K chunks for a fused 1x1 shortcut (ResnetBlock2D.conv_shortcut over the RAW block input): centre tap only,
 // loaded through a second tensor map and passed through the transform stage untouched.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent; registers re-balanced with setmaxnreg):
-//   warps 0..3   : epilogue (staged + TMA store, or direct for fp32 maps) — same code as the tap-streaming kernel
-//   warp 4       : patch producer (TMA)           warp 7 : weight producer (TMA, one box per (chunk, tap))
-//   warps 5 (,6) : MMA issuers, one per image row of the tile (MT = TH = 1 or 2); warp 6 also owns the TMEM allocation
-//   warps 8..11  : operand transform (GroupNorm scale/shift + SiLU in place, or pass-through)
+// Warp roles (384 threads, 1 CTA / SM, persistent).  Default build (XFORM = false): warps 0..7 epilogue (as in igemm.cu),
+// warp 8 patch producer (TMA), warps 9 (,10) MMA issuers — one per image row of the tile (MT = TH = 1 or 2), warp 10 also
+// owns the TMEM allocation —, warp 11 weight producer (one TMA box per (chunk, tap)).  GroupNorm-transform build
+// (XFORM = true, GP_GN_FUSE=1): warps 0..3 epilogue, 4..7 the same roles, 8..11 operand transform (GroupNorm scale/shift +
+// SiLU in place); registers re-balanced with setmaxnreg.
 #include <cstdlib>
 
 #include "igemm_common.cuh"
