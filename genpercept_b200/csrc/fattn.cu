@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace gp {
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1) fattn_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // see ptx.cuh: the next kernel may be scheduled; it blocks in its own pdl_wait
+  pdl_wait();         // set-up done; the predecessor grid has completed before any of its outputs is read
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
@@ -400,11 +403,11 @@ cudaError_t fattn_launch(const FattnParams& p_in, cudaStream_t stream) {
   const int grid = p.B * p.heads * ((p.q_tiles + 1) / 2);
   if (grid <= 0) return cudaSuccess;
   if (p.bf16) {
-    if (poly) fattn_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(p);
-    else fattn_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+    if (poly) launch(fattn_kernel<true, true>, grid, kThreads, kSmemBytes, stream, p);
+    else launch(fattn_kernel<true, false>, grid, kThreads, kSmemBytes, stream, p);
   } else {
-    if (poly) fattn_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(p);
-    else fattn_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+    if (poly) launch(fattn_kernel<false, true>, grid, kThreads, kSmemBytes, stream, p);
+    else launch(fattn_kernel<false, false>, grid, kThreads, kSmemBytes, stream, p);
   }
   return cudaGetLastError();
 }

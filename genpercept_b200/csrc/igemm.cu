@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "igemm_common.cuh"
+#include "launch.h"
 
 namespace gp {
 
@@ -70,6 +71,8 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // the next kernel of the stream may be scheduled (it blocks in its own pdl_wait until this grid is done)
+  pdl_wait();         // barriers / TMEM are set up; from here on the predecessor's outputs are read
 
   // Single-thread roles run warp-uniform (every lane walks the loop and waits on the barriers) and one
   // elected lane issues: the TMA coordinates / UMMA descriptors then stay in uniform registers.
@@ -338,9 +341,9 @@ cudaError_t igemm_launch(const IgemmParams& p, cudaStream_t stream) {
   const size_t smem = kMaxSmem;
   if (p.patch) return igemm_patch_launch(p, grid, stream);
   if (p.flags & IG_BF16) {
-    igemm_kernel<true><<<grid, kTapThreads, smem, stream>>>(p);
+    launch(igemm_kernel<true>, grid, kTapThreads, smem, stream, p);
   } else {
-    igemm_kernel<false><<<grid, kTapThreads, smem, stream>>>(p);
+    launch(igemm_kernel<false>, grid, kTapThreads, smem, stream, p);
   }
   return cudaGetLastError();
 }

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "igemm_common.cuh"
+#include "launch.h"
 
 namespace gp {
 
@@ -110,6 +111,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // see ptx.cuh: the next kernel may be scheduled; it blocks in its own pdl_wait
+  pdl_wait();         // set-up done; the predecessor grid has completed before any of its outputs is read
 
   if (warp < NE) {
     // ===================================================================== epilogue
@@ -373,11 +376,11 @@ cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t s
   }
   const bool xform = p.gn_ss != nullptr;
   if (p.flags & IG_BF16) {
-    if (xform) igemm_patch_kernel<true, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
-    else igemm_patch_kernel<true, false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+    if (xform) launch(igemm_patch_kernel<true, true>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else launch(igemm_patch_kernel<true, false>, grid, kPatchThreads, kMaxSmem, stream, p);
   } else {
-    if (xform) igemm_patch_kernel<false, true><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
-    else igemm_patch_kernel<false, false><<<grid, kPatchThreads, kMaxSmem, stream>>>(p);
+    if (xform) launch(igemm_patch_kernel<false, true>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else launch(igemm_patch_kernel<false, false>, grid, kPatchThreads, kMaxSmem, stream, p);
   }
   return cudaGetLastError();
 }

@@ -3,6 +3,11 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
+#include "launch.h"
+#include "ptx.cuh"
+
 namespace gp {
 namespace {
 
@@ -94,6 +99,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // ------------------------------------------------------------------------------ direct conv
 template <bool BF16>
 __global__ void direct_conv_kernel(const DirectConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -138,6 +145,8 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
 template <bool BF16>
 __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, int C, float* __restrict__ partial,
                                 int Ctot, int coff, int pix_per_block, int xs, int lo) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];   // [PIX][C][2]
   const int n = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -188,6 +197,8 @@ __global__ void gn_stats_kernel(const uint16_t* __restrict__ x, long long HW, in
 __global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc s0, GnSrc s1, int nsrc, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int N, int Ctot, int groups,
                                                           float inv_count, float eps, float* __restrict__ ss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -229,6 +240,8 @@ template <bool BF16, bool SILU>
 __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, int C, const float* __restrict__ ss,
                                 int Ctot, int coff, uint16_t* __restrict__ y, int y_cstride, int pix_per_block, int xs,
                                 int lo_x, int lo_y) {
+  pdl_trigger();
+  pdl_wait();
   // blockDim = (C/8 channel vectors, PIX pixel lanes); grid = (pixel chunks, N).  The thread's 8
   // (scale, shift) pairs live in registers for its whole pixel strip.
   const int n = blockIdx.y;
@@ -280,36 +293,55 @@ __global__ void gn_apply_kernel(const uint16_t* __restrict__ x, long long HW, in
 constexpr int kLnMaxVec = 5;   // C <= 1280
 // One warp per token; KV = 8-channel vectors per lane (2 for C <= 512, 3 for C <= 768, 5 for C <= 1280).  Sized to
 // the channel count the kernel keeps ~35 registers at C = 320 instead of 64 (r1_final: 1.2 TB/s at half occupancy).
-template <bool BF16, int KV>
+template <bool BF16, int KV, int TOK>
 __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens,
                                                         int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int lo) {
+  pdl_trigger();
+  pdl_wait();
+  // TOK tokens per warp: all their loads are issued before the first reduction (one token per warp left the warp
+  // with a single 16-byte load per lane in flight: 2.2 TB/s on the 94 MB maps of the UNet's first level, r2)
   const int lane = threadIdx.x & 31;
-  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tok >= tokens) return;
+  const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
+  if (tok0 >= tokens) return;
   const int nvec = C / 8;
   const int xs = lo ? 2 * C : C;
-  float f[KV][8];
-  float s = 0.f;
+  float f[TOK][KV][8];
 #pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-      load8<BF16>(x + tok * xs + v * 8, lo, f[i]);
+  for (int t = 0; t < TOK; ++t) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += f[i][e];
+    for (int i = 0; i < KV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec && tok0 + t < tokens) {
+        load8<BF16>(x + (tok0 + t) * xs + v * 8, lo, f[t][i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[t][i][e] = 0.f;
+      }
     }
   }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
+  float mean[TOK], rstd[TOK];
 #pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    if (lane + 32 * i < nvec) {
+  for (int t = 0; t < TOK; ++t) {
+    float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q += d * d; }
+    for (int i = 0; i < KV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += f[t][i][e];
+      }
     }
+    mean[t] = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[t][i][e] - mean[t]; q += d * d; }
+      }
+    }
+    rstd[t] = rsqrtf(warp_sum(q) / C + eps);
   }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
 #pragma unroll
   for (int i = 0; i < KV; ++i) {
     const int v = lane + 32 * i;
@@ -318,10 +350,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
       const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
-      store8<BF16>(y + tok * xs + v * 8, lo, o);
+      for (int t = 0; t < TOK; ++t) {
+        if (tok0 + t < tokens) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (f[t][i][e] - mean[t]) * rstd[t] * gg[e] + bb[e];
+          store8<BF16>(y + (tok0 + t) * xs + v * 8, lo, o);
+        }
+      }
     }
   }
 }
@@ -330,6 +367,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
 constexpr int kSmMaxVec = 8;   // T <= 256 threads * 8 vec * 8 = 16384
 template <bool BF16>
 __global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long rows, int T, int Tp, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -348,6 +387,8 @@ __global__ void softmax_rows_small_kernel(uint16_t* __restrict__ s, long long ro
 // VAE mid-block rows (T = 9216) then hold 24 values per thread instead of 64 (r1_final: 2.5 TB/s at low occupancy).
 template <bool BF16, int MV>
 __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp, int lo) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   uint16_t* row = s + (long long)blockIdx.x * (lo ? 2 * Tp : Tp);
   const int nvec = T / 8;
@@ -394,6 +435,102 @@ __global__ void softmax_rows_kernel(uint16_t* __restrict__ s, int T, int Tp, int
   }
 }
 
+// Long rows (the VAE mid-block attention, T = 9216: 18 KiB per row, 73 728 rows per step and attention): a persistent
+// CTA streams its rows through a 3-slot shared-memory ring with bulk async copies — slot k + 2 is loading and slot
+// k - 1 is draining to global memory while row k is reduced in registers — so each SM keeps several rows in flight in
+// both directions.  The one-row-per-CTA kernel above has its loads, two block reductions and stores back to back
+// (r2: 2.4 TB/s, 1.1 ms per attention; this one is bound by the copy rate).
+constexpr int kSmPipeThreads = 384;
+constexpr int kSmPipeSlots = 3;
+template <bool BF16, int MV>
+__global__ void __launch_bounds__(kSmPipeThreads) softmax_rows_pipe_kernel(uint16_t* __restrict__ s, long long rows, int T, int Tp) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  __shared__ float red[2][kSmPipeThreads / 32];
+  __shared__ __align__(8) uint64_t full[kSmPipeSlots];
+  const int row_bytes = T * 2;
+  const int slot_bytes = (row_bytes + 127) & ~127;
+  const int nvec = T / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kSmPipeThreads / 32;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSmPipeSlots; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](long long k) {            // thread 0 only
+    const long long r = (long long)blockIdx.x + k * gridDim.x;
+    if (r >= rows) return;
+    const int slot = (int)(k % kSmPipeSlots);
+    mbar_expect_tx(&full[slot], (uint32_t)row_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm_raw + (size_t)slot * slot_bytes)),
+                 "l"(reinterpret_cast<uint64_t>(s + r * Tp)), "r"(row_bytes), "r"(smem_u32(&full[slot]))
+                 : "memory");
+  };
+  if (threadIdx.x == 0) { issue_load(0); issue_load(1); }
+  long long k = 0;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x, ++k) {
+    const int slot = (int)(k % kSmPipeSlots);
+    uint8_t* buf = sm_raw + (size_t)slot * slot_bytes;
+    mbar_wait(&full[slot], (uint32_t)((k / kSmPipeSlots) & 1), 30);
+    float f[MV][8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MV; ++i) {
+      const int v = threadIdx.x + i * kSmPipeThreads;
+      if (v < nvec) {
+        unpack8<BF16>(*reinterpret_cast<const uint4*>(buf + v * 16), f[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m = fmaxf(m, f[i][e]);
+      }
+    }
+    m = warp_max(m);
+    if (lane == 0) red[0][warp] = m;
+    __syncthreads();
+    m = red[0][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, red[0][w]);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MV; ++i) {
+      if (threadIdx.x + i * kSmPipeThreads < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { f[i][e] = __expf(f[i][e] - m); sum += f[i][e]; }
+      }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[1][warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sum += red[1][w];
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < MV; ++i) {
+      const int v = threadIdx.x + i * kSmPipeThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[i][e] *= inv;
+        *reinterpret_cast<uint4*>(buf + v * 16) = pack8<BF16>(f[i]);
+      }
+    }
+    fence_proxy_async_shared();                   // the generic-proxy writes above are visible to the bulk store
+    __syncthreads();                              // (also: red[] is free for the next row)
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(s + r * Tp)),
+                   "r"(smem_u32(buf)), "r"(row_bytes)
+                   : "memory");
+      tma_store_commit();
+      // slot of row k + 2 == slot of row k - 1: its store (the group before the one just committed) has read the slot
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      issue_load(k + 2);
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------ 2-token cross attention
 // y = x + c0 + sigmoid(LN(x).U + u0).M : one warp handles TOK tokens at once so every U / M / c0 vector
 // fetched from L1/L2 is reused TOK times (the single-token version re-read ~2*heads*C*4 bytes per token).
@@ -401,6 +538,8 @@ template <bool BF16, int KV, int TOK>
 __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens, int C,
                               int heads, const float* __restrict__ U, const float* __restrict__ u0,
                               const float* __restrict__ M, const float* __restrict__ c0, float eps, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
   if (tok0 >= tokens) return;
@@ -497,9 +636,135 @@ __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restri
   }
 }
 
+// Same operator with the folded weights resident in shared memory.  The kernel above re-reads U and M (2 * heads * C
+// floats: 12.8 / 51 / 205 KB at C = 320 / 640 / 1280) through L1 for every warp's tokens — 0.94 GB of L2 traffic per
+// launch at every level, 100-160 us for a 6-94 MB activation (r2 per-op events).  Here a persistent CTA loads them once,
+// its warps loop over token groups, and the heads are taken five at a time so that the five warp reductions and
+// sigmoids of a batch are independent chains instead of one serial chain per head.
+constexpr int kXaHB = 5;
+template <bool BF16, int KV, int TOK>
+__global__ void __launch_bounds__(256) xattn2_smem_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens,
+                                                          int C, int heads, const float* __restrict__ U,
+                                                          const float* __restrict__ u0, const float* __restrict__ M,
+                                                          const float* __restrict__ c0, float eps, int lo) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float xa_sm[];
+  float* sU = xa_sm;
+  float* sM = sU + heads * C;
+  float* sc0 = sM + heads * C;
+  float* su0 = sc0 + C;
+  {
+    const int n4 = heads * C / 4;
+    const float4* gU = reinterpret_cast<const float4*>(U);
+    const float4* gM = reinterpret_cast<const float4*>(M);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      reinterpret_cast<float4*>(sU)[i] = __ldg(gU + i);
+      reinterpret_cast<float4*>(sM)[i] = __ldg(gM + i);
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sc0[i] = __ldg(c0 + i);
+    for (int i = threadIdx.x; i < heads; i += blockDim.x) su0[i] = __ldg(u0 + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nvec = C / 8;
+  const int xs = lo ? 2 * C : C;
+  for (long long tok0 = ((long long)blockIdx.x * nwarp + warp) * TOK; tok0 < tokens; tok0 += (long long)gridDim.x * nwarp * TOK) {
+    float g[TOK][KV][8], acc[TOK][KV][8];
+    float rstd[TOK];
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+      const bool tv = tok0 + t < tokens;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec && tv) {
+          load8<BF16>(x + (tok0 + t) * xs + v * 8, lo, g[t][i]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[t][i][e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += g[t][i][e];
+      }
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+          const float4 a = *reinterpret_cast<const float4*>(sc0 + v * 8), b = *reinterpret_cast<const float4*>(sc0 + v * 8 + 4);
+          const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[t][i][e] = g[t][i][e] + cc[e];
+            g[t][i][e] -= mean;
+            q += g[t][i][e] * g[t][i][e];
+          }
+        }
+      }
+      rstd[t] = rsqrtf(warp_sum(q) / C + eps);
+    }
+    for (int h0 = 0; h0 < heads; h0 += kXaHB) {
+      float d[kXaHB][TOK];
+#pragma unroll
+      for (int hh = 0; hh < kXaHB; ++hh) {
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) d[hh][t] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            const float* up = sU + (h0 + hh) * C + v * 8;
+            const float4 a = *reinterpret_cast<const float4*>(up), b = *reinterpret_cast<const float4*>(up + 4);
+#pragma unroll
+            for (int t = 0; t < TOK; ++t)
+              d[hh][t] += g[t][i][0] * a.x + g[t][i][1] * a.y + g[t][i][2] * a.z + g[t][i][3] * a.w + g[t][i][4] * b.x +
+                          g[t][i][5] * b.y + g[t][i][6] * b.z + g[t][i][7] * b.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < kXaHB; ++hh)
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) d[hh][t] = 1.f / (1.f + __expf(-(warp_sum(d[hh][t]) * rstd[t] + su0[h0 + hh])));
+#pragma unroll
+      for (int hh = 0; hh < kXaHB; ++hh) {
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            const float* mp = sM + (h0 + hh) * C + v * 8;
+            const float4 a = *reinterpret_cast<const float4*>(mp), b = *reinterpret_cast<const float4*>(mp + 4);
+#pragma unroll
+            for (int t = 0; t < TOK; ++t) {
+              const float pr = d[hh][t];
+              acc[t][i][0] += pr * a.x; acc[t][i][1] += pr * a.y; acc[t][i][2] += pr * a.z; acc[t][i][3] += pr * a.w;
+              acc[t][i][4] += pr * b.x; acc[t][i][5] += pr * b.y; acc[t][i][6] += pr * b.z; acc[t][i][7] += pr * b.w;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+      if (tok0 + t < tokens) {
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) store8<BF16>(y + (tok0 + t) * xs + v * 8, lo, acc[t][i]);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ elementwise
 template <bool BF16>
 __global__ void geglu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec, int C4) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C4 / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -517,6 +782,8 @@ __global__ void geglu_kernel(const uint16_t* __restrict__ in, uint16_t* __restri
 template <bool BF16>
 __global__ void relu_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long total_vec, int nvec,
                             int lo) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
     const long long off = lo ? (i / nvec) * (2LL * lo) + (i % nvec) * 8 : i * 8;   // [pixel][hi C | lo C]
@@ -531,6 +798,8 @@ __global__ void relu_kernel(const uint16_t* __restrict__ in, uint16_t* __restric
 template <bool BF16>
 __global__ void bilinear_up2x_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W,
                                      int C, float sy, float sx, long long total_vec, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const int xs = lo ? 2 * C : C;
@@ -561,6 +830,8 @@ __global__ void bilinear_up2x_kernel(const uint16_t* __restrict__ in, uint16_t* 
 template <bool BF16>
 __global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_t* __restrict__ out, int N,
                                   long long HW, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
   const int n = (int)(i / HW);
@@ -583,6 +854,8 @@ __global__ void preprocess_kernel(const void* __restrict__ in, int kind, uint16_
 template <bool BF16>
 __global__ void preprocess_im2col_kernel(const void* __restrict__ in, int kind, uint16_t* __restrict__ out, int N, int H, int W,
                                          int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long HW = (long long)H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
@@ -626,10 +899,14 @@ __device__ __forceinline__ float ord2f(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 __global__ void minmax_init_kernel(unsigned int* s, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) { s[2 * i] = 0xFFFFFFFFu; s[2 * i + 1] = 0u; }
 }
 __global__ void minmax_reduce_kernel(const float* __restrict__ x, long long HW, unsigned int* s) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   float mn = INFINITY, mx = -INFINITY;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
@@ -640,6 +917,8 @@ __global__ void minmax_reduce_kernel(const float* __restrict__ x, long long HW, 
   if ((threadIdx.x & 31) == 0) { atomicMin(&s[2 * n], f2ord(mn)); atomicMax(&s[2 * n + 1], f2ord(mx)); }
 }
 __global__ void minmax_apply_kernel(float* __restrict__ x, long long HW, const unsigned int* __restrict__ s, float dmin, int zero_min) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const float mn = zero_min ? 0.f : ord2f(s[2 * n]), mx = ord2f(s[2 * n + 1]);
   const float d = fmaxf(mx - mn, dmin);
@@ -672,7 +951,7 @@ cudaError_t direct_conv(const DirectConvParams& p, bool bf16, cudaStream_t s) {
   if (total <= 0) return cudaSuccess;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  GP_DISPATCH_BF16(bf16, (direct_conv_kernel<BF><<<(unsigned)blocks, threads, 0, s>>>(p)));
+  GP_DISPATCH_BF16(bf16, (launch(direct_conv_kernel<BF>, (unsigned)blocks, threads, 0, s, p)));
   return cudaGetLastError();
 }
 
@@ -694,7 +973,7 @@ cudaError_t gn_stats(const void* x, int N, long long HW, int C, float* partial, 
   dim3 block(nvec, pix);
   dim3 grid((unsigned)chunks, N);
   const size_t smem = (size_t)pix * C * 2 * sizeof(float);
-  GP_DISPATCH_BF16(bf16, (gn_stats_kernel<BF><<<grid, block, smem, s>>>(reinterpret_cast<const uint16_t*>(x), HW, C,
+  GP_DISPATCH_BF16(bf16, (launch(gn_stats_kernel<BF>, grid, block, smem, s, reinterpret_cast<const uint16_t*>(x), HW, C,
                                                                          partial, Ctot, coff, pix_per_block,
                                                                          split ? 2 * C : C, split ? C : 0)));
   return cudaGetLastError();
@@ -704,7 +983,7 @@ cudaError_t gn_finalize(const GnSrc* srcs, int nsrc, const float* gamma, const f
                         int groups, long long HW, float eps, float* ss, cudaStream_t s) {
   if (nsrc < 1 || nsrc > 2) return cudaErrorInvalidValue;
   const float inv_count = 1.0f / ((float)HW * (float)(Ctot / groups));
-  gn_finalize_kernel<<<N * groups, 256, 0, s>>>(srcs[0], nsrc > 1 ? srcs[1] : srcs[0], nsrc, gamma, beta, N, Ctot,
+  launch(gn_finalize_kernel, N * groups, 256, 0, s, srcs[0], nsrc > 1 ? srcs[1] : srcs[0], nsrc, gamma, beta, N, Ctot,
                                                        groups, inv_count, eps, ss);
   return cudaGetLastError();
 }
@@ -724,9 +1003,9 @@ cudaError_t gn_apply(const void* x, int N, long long HW, int C, const float* ss,
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   if (silu)
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, true><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
+    GP_DISPATCH_BF16(bf16, (launch(gn_apply_kernel<BF, true>, grid, block, 0, s, xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
   else
-    GP_DISPATCH_BF16(bf16, (gn_apply_kernel<BF, false><<<grid, block, 0, s>>>(xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
+    GP_DISPATCH_BF16(bf16, (launch(gn_apply_kernel<BF, false>, grid, block, 0, s, xi, HW, C, ss, Ctot, coff, yo, y_cstride, pix_per_block, xs, lo_x, lo_y)));
   return cudaGetLastError();
 }
 
@@ -735,16 +1014,22 @@ cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const flo
   const int lo = split ? C : 0;
   if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
   const int tpb = 8;
-  const long long blocks = (tokens + tpb - 1) / tpb;
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   const int kv = (C / 8 + 31) / 32;
-  if (kv <= 2)
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 2><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
+  static const bool ln_tok2 = [] { const char* v = getenv("GP_LN_TOK"); return v && v[0] == '2'; }();   // A/B switch
+  const int tok = (ln_tok2 && kv <= 3) ? 2 : 1;
+  const long long blocks = (tokens + tpb * tok - 1) / (tpb * tok);
+  if (tok == 1 && kv <= 2)
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 2, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
+  else if (tok == 1 && kv <= 3)
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 3, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
+  else if (kv <= 2)
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 2, 2>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   else if (kv <= 3)
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 3><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 3, 2>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   else
-    GP_DISPATCH_BF16(bf16, (layernorm_kernel<BF, 5><<<(unsigned)blocks, tpb * 32, 0, s>>>(xi, yo, tokens, C, gamma, beta, eps, lo)));
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 5, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   return cudaGetLastError();
 }
 
@@ -752,19 +1037,45 @@ cudaError_t softmax_rows(void* sio, long long rows, int T, int Tp, bool bf16, cu
   const int lo = split ? Tp : 0;
   if (T % 8 || Tp % 8 || T < 64) {
     const int wpb = 8;
-    GP_DISPATCH_BF16(bf16, (softmax_rows_small_kernel<BF><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+    GP_DISPATCH_BF16(bf16, (launch(softmax_rows_small_kernel<BF>, (unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s, 
                                reinterpret_cast<uint16_t*>(sio), rows, T, Tp, lo)));
     return cudaGetLastError();
   }
   if (T / 8 > 256 * kSmMaxVec) return cudaErrorInvalidValue;
+  static const bool no_pipe = [] { const char* e = getenv("GP_SOFTMAX_PIPE"); return e && e[0] == '0'; }();
+  if (!split && !no_pipe && T >= 2048 && T / 8 <= kSmPipeThreads * 6 && rows >= 1024) {
+    const int slot_bytes = (T * 2 + 127) & ~127;
+    const int smem = kSmPipeSlots * slot_bytes;
+    if (smem <= 200 * 1024) {
+      static int sms[64] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!sms[dev & 63]) {
+        cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+        GP_DISPATCH_BF16(bf16, (cudaFuncSetAttribute(softmax_rows_pipe_kernel<BF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+        GP_DISPATCH_BF16(bf16, (cudaFuncSetAttribute(softmax_rows_pipe_kernel<BF, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+      }
+      int per_sm = (220 * 1024) / (smem + 1024);
+      if (per_sm > 5) per_sm = 5;                 // 5 x 384 threads
+      if (per_sm < 1) per_sm = 1;
+      long long grid = (long long)sms[dev & 63] * per_sm;
+      if (grid > rows) grid = rows;
+      if (T / 8 <= kSmPipeThreads * 3) {
+        GP_DISPATCH_BF16(bf16, (launch(softmax_rows_pipe_kernel<BF, 3>, (unsigned)grid, kSmPipeThreads, smem, s, reinterpret_cast<uint16_t*>(sio), rows, T, Tp)));
+      } else {
+        GP_DISPATCH_BF16(bf16, (launch(softmax_rows_pipe_kernel<BF, 6>, (unsigned)grid, kSmPipeThreads, smem, s, reinterpret_cast<uint16_t*>(sio), rows, T, Tp)));
+      }
+      return cudaGetLastError();
+    }
+  }
   int threads = ((T / 8 + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
   if (T / 8 > 256 && T / 8 <= 512 * 3) {
-    GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, 3><<<(unsigned)rows, 512, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
+    GP_DISPATCH_BF16(bf16, (launch(softmax_rows_kernel<BF, 3>, (unsigned)rows, 512, 0, s, reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
     return cudaGetLastError();
   }
-  GP_DISPATCH_BF16(bf16, (softmax_rows_kernel<BF, kSmMaxVec><<<(unsigned)rows, threads, 0, s>>>(reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
+  GP_DISPATCH_BF16(bf16, (launch(softmax_rows_kernel<BF, kSmMaxVec>, (unsigned)rows, threads, 0, s, reinterpret_cast<uint16_t*>(sio), T, Tp, lo)));
   return cudaGetLastError();
 }
 
@@ -774,7 +1085,7 @@ static cudaError_t xattn2_launch(const void* x, void* y, long long tokens, int C
   const int wpb = 8;
   const long long per_block = (long long)wpb * TOK;
   const long long blocks = (tokens + per_block - 1) / per_block;
-  xattn2_kernel<BF, KV, TOK><<<(unsigned)blocks, wpb * 32, 0, s>>>(reinterpret_cast<const uint16_t*>(x),
+  launch(xattn2_kernel<BF, KV, TOK>, (unsigned)blocks, wpb * 32, 0, s, reinterpret_cast<const uint16_t*>(x),
                                                                     reinterpret_cast<uint16_t*>(y), tokens, C, heads, U, u0, M,
                                                                     c0, eps, lo);
   return cudaGetLastError();
@@ -786,6 +1097,35 @@ cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, c
   if (C % 8 || C / 8 > 32 * kLnMaxVec) return cudaErrorInvalidValue;
   const int kv = (C / 8 + 31) / 32;
   cudaError_t e = cudaSuccess;
+  static const bool no_smem = [] { const char* v = getenv("GP_XATTN_SMEM"); return v && v[0] == '0'; }();
+  const size_t smem = ((size_t)2 * heads * C + C + heads) * sizeof(float);
+  if (!no_smem && heads % kXaHB == 0 && C % 32 == 0 && smem <= 226 * 1024) {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sms[dev & 63]) {
+      const int big = 226 * 1024;
+      GP_DISPATCH_BF16(bf16, (cudaFuncSetAttribute(xattn2_smem_kernel<BF, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+      GP_DISPATCH_BF16(bf16, (cudaFuncSetAttribute(xattn2_smem_kernel<BF, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+      GP_DISPATCH_BF16(bf16, (cudaFuncSetAttribute(xattn2_smem_kernel<BF, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+      cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;                       // 256 threads at <= 128 registers
+    if (per_sm < 1) per_sm = 1;
+    const int tok = kv <= 3 ? 2 : 1;
+    long long grid = (tokens + 8 * tok - 1) / (8 * tok);
+    if (grid > (long long)sms[dev & 63] * per_sm) grid = (long long)sms[dev & 63] * per_sm;
+    const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
+    uint16_t* yo = reinterpret_cast<uint16_t*>(y);
+    if (kv <= 2)
+      GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 2, 2>, (unsigned)grid, 256, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
+    else if (kv <= 3)
+      GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 3, 2>, (unsigned)grid, 256, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
+    else
+      GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 5, 1>, (unsigned)grid, 256, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
+    return cudaGetLastError();
+  }
   if (kv <= 2)
     GP_DISPATCH_BF16(bf16, (e = xattn2_launch<BF, 2, 2>(x, y, tokens, C, heads, U, u0, M, c0, eps, s, lo)));
   else if (kv <= 3)
@@ -797,14 +1137,14 @@ cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, c
 
 cudaError_t geglu(const void* in, void* out, long long tokens, int C4, bool bf16, cudaStream_t s) {
   const long long total_vec = tokens * (C4 / 8);
-  GP_DISPATCH_BF16(bf16, (geglu_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(geglu_kernel<BF>, blocks_for(total_vec, 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec, C4)));
   return cudaGetLastError();
 }
 
 cudaError_t relu16(const void* in, void* out, long long n, bool bf16, cudaStream_t s, int split_c) {
   const long long total_vec = n / 8;        // n = pixels * C logical elements
-  GP_DISPATCH_BF16(bf16, (relu_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(relu_kernel<BF>, blocks_for(total_vec, 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), total_vec,
                              split_c ? split_c / 8 : 1, split_c)));
   return cudaGetLastError();
@@ -814,7 +1154,7 @@ cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C,
   const long long total_vec = (long long)N * 4 * H * W * (C / 8);
   const float sy = H > 1 ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float sx = W > 1 ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-  GP_DISPATCH_BF16(bf16, (bilinear_up2x_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(bilinear_up2x_kernel<BF>, blocks_for(total_vec, 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, C, sy,
                              sx, total_vec, split ? C : 0)));
   return cudaGetLastError();
@@ -823,7 +1163,7 @@ cudaError_t bilinear_up2x(const void* in, void* out, int N, int H, int W, int C,
 cudaError_t preprocess_rgb(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s, bool split) {
   const long long HW = (long long)H * W;
   const long long total = (long long)N * HW;
-  GP_DISPATCH_BF16(bf16, (preprocess_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(preprocess_kernel<BF>, (unsigned)((total + 255) / 256), 256, 0, s, 
                              in, in_kind, reinterpret_cast<uint16_t*>(out), N, HW, split ? 8 : 0)));
   return cudaGetLastError();
 }
@@ -832,6 +1172,8 @@ namespace {
 // 16-bit NHWC8 (first `c` channels) -> fp32 NCHW [N, c, H, W]
 template <bool BF16>
 __global__ void nhwc8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int N, long long HW, int c, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
   const int n = (int)(i / HW);
@@ -847,6 +1189,8 @@ __global__ void nhwc8_to_nchw_kernel(const uint16_t* __restrict__ in, float* __r
 template <bool BF16>
 __global__ void nchw4_affine_to_nhwc8_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, long long HW,
                                              float pre, const float* __restrict__ m, const float* __restrict__ b, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
   const int n = (int)(i / HW);
@@ -875,6 +1219,8 @@ namespace {
 template <bool BF16>
 __global__ void latent_pack_kernel(const uint16_t* __restrict__ lat, const uint16_t* __restrict__ smp, uint16_t* __restrict__ xin,
                                    long long npx, int in_ch, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npx) return;
   const long long o = i * (lo ? 16 : 8);
@@ -895,6 +1241,8 @@ __global__ void latent_pack_kernel(const uint16_t* __restrict__ lat, const uint1
 template <bool BF16>
 __global__ void ddim_step_kernel(const uint16_t* __restrict__ mo, uint16_t* __restrict__ smp, uint16_t* __restrict__ x0, long long npx,
                                  float c0, float c1, float c2, float c3, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npx) return;
   const long long o = i * (lo ? 16 : 8);
@@ -913,6 +1261,8 @@ __global__ void ddim_step_kernel(const uint16_t* __restrict__ mo, uint16_t* __re
 template <bool BF16>
 __global__ void latent_affine_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long npx, float pre,
                                      const float* __restrict__ mat, const float* __restrict__ bias, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npx) return;
   const long long o = i * (lo ? 16 : 8);
@@ -930,20 +1280,20 @@ __global__ void latent_affine_kernel(const uint16_t* __restrict__ in, uint16_t* 
 }  // namespace
 
 cudaError_t latent_pack(const void* lat, const void* smp, void* xin, long long npx, int in_ch, bool bf16, cudaStream_t s, bool split) {
-  GP_DISPATCH_BF16(bf16, (latent_pack_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(latent_pack_kernel<BF>, (unsigned)((npx + 255) / 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(lat), reinterpret_cast<const uint16_t*>(smp),
                              reinterpret_cast<uint16_t*>(xin), npx, in_ch, split ? 8 : 0)));
   return cudaGetLastError();
 }
 cudaError_t ddim_step(const void* model_out, void* sample, void* x0, long long npx, const float c[4], bool bf16, cudaStream_t s, bool split) {
-  GP_DISPATCH_BF16(bf16, (ddim_step_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(ddim_step_kernel<BF>, (unsigned)((npx + 255) / 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(model_out), reinterpret_cast<uint16_t*>(sample),
                              reinterpret_cast<uint16_t*>(x0), npx, c[0], c[1], c[2], c[3], split ? 8 : 0)));
   return cudaGetLastError();
 }
 cudaError_t latent_affine(const void* in, void* out, long long npx, float pre, const float* mat, const float* bias, bool bf16,
                           cudaStream_t s, bool split) {
-  GP_DISPATCH_BF16(bf16, (latent_affine_kernel<BF><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(latent_affine_kernel<BF>, (unsigned)((npx + 255) / 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), npx, pre, mat, bias,
                              split ? 8 : 0)));
   return cudaGetLastError();
@@ -951,7 +1301,7 @@ cudaError_t latent_affine(const void* in, void* out, long long npx, float pre, c
 
 cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, int c, bool bf16, cudaStream_t s, bool split) {
   const long long HW = (long long)H * W, total = (long long)N * HW;
-  GP_DISPATCH_BF16(bf16, (nhwc8_to_nchw_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(nhwc8_to_nchw_kernel<BF>, (unsigned)((total + 255) / 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), out, N, HW, c, split ? 8 : 0)));
   return cudaGetLastError();
 }
@@ -959,25 +1309,25 @@ cudaError_t nhwc8_to_nchw_f32(const void* in, float* out, int N, int H, int W, i
 cudaError_t nchw4_affine_to_nhwc8(const float* in, void* out, int N, int H, int W, float pre, const float* m, const float* b,
                                   bool bf16, cudaStream_t s, bool split) {
   const long long HW = (long long)H * W, total = (long long)N * HW;
-  GP_DISPATCH_BF16(bf16, (nchw4_affine_to_nhwc8_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(nchw4_affine_to_nhwc8_kernel<BF>, (unsigned)((total + 255) / 256), 256, 0, s, 
                              in, reinterpret_cast<uint16_t*>(out), N, HW, pre, m, b, split ? 8 : 0)));
   return cudaGetLastError();
 }
 
 cudaError_t preprocess_rgb_im2col(const void* in, int in_kind, void* out, int N, int H, int W, bool bf16, cudaStream_t s, bool split) {
   const long long total = (long long)N * H * W;
-  GP_DISPATCH_BF16(bf16, (preprocess_im2col_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(preprocess_im2col_kernel<BF>, (unsigned)((total + 127) / 128), 128, 0, s, 
                              in, in_kind, reinterpret_cast<uint16_t*>(out), N, H, W, split ? 32 : 0)));
   return cudaGetLastError();
 }
 
 cudaError_t minmax_normalize(float* x, int N, long long HW, unsigned int* scratch, cudaStream_t s, float dmin, bool zero_min) {
-  minmax_init_kernel<<<(N + 63) / 64, 64, 0, s>>>(scratch, N);
+  launch(minmax_init_kernel, (N + 63) / 64, 64, 0, s, scratch, N);
   int bx = (int)((HW + 256 * 8 - 1) / (256 * 8));
   if (bx > 256) bx = 256;
   if (bx < 1) bx = 1;
-  minmax_reduce_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch);
-  minmax_apply_kernel<<<dim3(bx, N), 256, 0, s>>>(x, HW, scratch, dmin, zero_min ? 1 : 0);
+  launch(minmax_reduce_kernel, dim3(bx, N), 256, 0, s, x, HW, scratch);
+  launch(minmax_apply_kernel, dim3(bx, N), 256, 0, s, x, HW, scratch, dmin, zero_min ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -986,6 +1336,8 @@ namespace {
 // median (torch.median: the LOWER middle value for an even count) or mean.
 __global__ void ensemble_reduce_kernel(const float* __restrict__ d, int B, long long HW, const float* __restrict__ sc,
                                        const float* __restrict__ sh, int median, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   float v[32];
@@ -1004,13 +1356,15 @@ __global__ void ensemble_reduce_kernel(const float* __restrict__ d, int B, long 
 cudaError_t ensemble_reduce(const float* d, int B, long long HW, const float* scale_dev, const float* shift_dev, bool median, float* out,
                             cudaStream_t s) {
   if (B < 1 || B > 32) return cudaErrorInvalidValue;
-  ensemble_reduce_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s>>>(d, B, HW, scale_dev, shift_dev, median ? 1 : 0, out);
+  launch(ensemble_reduce_kernel, (unsigned)((HW + 255) / 256), 256, 0, s, d, B, HW, scale_dev, shift_dev, median ? 1 : 0, out);
   return cudaGetLastError();
 }
 
 namespace {
 __global__ void nearest_resize_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int OH,
                                       int OW, int nvec, float sy, float sx, long long total_vec) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % nvec);
@@ -1028,6 +1382,8 @@ __global__ void nearest_resize_kernel(const uint4* __restrict__ in, uint4* __res
 namespace {
 template <bool BF16>
 __global__ void softmax_groups_kernel(uint16_t* __restrict__ x, long long rows, int ld, int groups, int n, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * groups) return;
   uint16_t* p = x + (i / groups) * (lo ? 2 * ld : ld) + (i % groups) * n;
@@ -1043,7 +1399,7 @@ __global__ void softmax_groups_kernel(uint16_t* __restrict__ x, long long rows, 
 cudaError_t softmax_groups(void* x, long long rows, int ld, int groups, int n, bool bf16, cudaStream_t s, bool split) {
   if (groups < 1 || n < 1 || groups * n > ld) return cudaErrorInvalidValue;
   const long long total = rows * groups;
-  GP_DISPATCH_BF16(bf16, (softmax_groups_kernel<BF><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(softmax_groups_kernel<BF>, (unsigned)((total + 127) / 128), 128, 0, s, 
                              reinterpret_cast<uint16_t*>(x), rows, ld, groups, n, split ? ld : 0)));
   return cudaGetLastError();
 }
@@ -1053,6 +1409,8 @@ namespace {
 template <bool BF16>
 __global__ void bilinear_resize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W, int OH,
                                        int OW, int C, float sy, float sx, long long total_vec, int lo) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C / 8;
   const int xs = lo ? 2 * C : C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
@@ -1084,7 +1442,7 @@ cudaError_t bilinear_resize(const void* in, void* out, int N, int H, int W, int 
                             bool split) {
   if (C % 8) return cudaErrorInvalidValue;
   const long long total_vec = (long long)N * OH * OW * (C / 8);
-  GP_DISPATCH_BF16(bf16, (bilinear_resize_kernel<BF><<<blocks_for(total_vec, 256), 256, 0, s>>>(
+  GP_DISPATCH_BF16(bf16, (launch(bilinear_resize_kernel<BF>, blocks_for(total_vec, 256), 256, 0, s, 
                              reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, OH, OW, C,
                              (float)H / (float)OH, (float)W / (float)OW, total_vec, split ? C : 0)));
   return cudaGetLastError();
@@ -1093,7 +1451,7 @@ cudaError_t bilinear_resize(const void* in, void* out, int N, int H, int W, int 
 cudaError_t nearest_resize(const void* in, void* out, int N, int H, int W, int OH, int OW, int C, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   const long long total_vec = (long long)N * OH * OW * (C / 8);
-  nearest_resize_kernel<<<blocks_for(total_vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in),
+  launch(nearest_resize_kernel, blocks_for(total_vec, 256), 256, 0, s, reinterpret_cast<const uint4*>(in),
                                                                   reinterpret_cast<uint4*>(out), N, H, W, OH, OW, C / 8,
                                                                   (float)H / (float)OH, (float)W / (float)OW, total_vec);
   return cudaGetLastError();

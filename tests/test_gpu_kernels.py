@@ -204,7 +204,9 @@ def test_layernorm(tokens, C):
 
 
 @pytest.mark.parametrize("B,T,heads,d", [(2, 256, 5, 64), (1, 144, 20, 64), (1, 1024, 1, 512), (1, 16, 20, 64),
-                                         (2, 4, 20, 64), (1, 1, 20, 64), (1, 2304, 10, 64)])
+                                         (2, 4, 20, 64), (1, 1, 20, 64), (1, 2304, 10, 64),
+                                         # long d = 512 rows: the bulk-copy pipelined row softmax (3 / 6 vectors per thread)
+                                         (1, 2304, 1, 512), (1, 9216, 1, 512), (1, 9600, 1, 512)])
 def test_attention(B, T, heads, d):
     from genpercept_b200 import engine as E
     _setup()
