@@ -299,8 +299,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint16_t* __restri
                                                         float eps, int lo) {
   pdl_trigger();
   pdl_wait();
-  // TOK tokens per warp: all their loads are issued before the first reduction (one token per warp left the warp
-  // with a single 16-byte load per lane in flight: 2.2 TB/s on the 94 MB maps of the UNet's first level, r2)
   const int lane = threadIdx.x & 31;
   const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
   if (tok0 >= tokens) return;
@@ -643,7 +641,7 @@ __global__ void xattn2_kernel(const uint16_t* __restrict__ x, uint16_t* __restri
 // sigmoids of a batch are independent chains instead of one serial chain per head.
 constexpr int kXaHB = 5;
 template <bool BF16, int KV, int TOK>
-__global__ void __launch_bounds__(256) xattn2_smem_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens,
+__global__ void __launch_bounds__(KV >= 5 ? 512 : 256) xattn2_smem_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long tokens,
                                                           int C, int heads, const float* __restrict__ U,
                                                           const float* __restrict__ u0, const float* __restrict__ M,
                                                           const float* __restrict__ c0, float eps, int lo) {
@@ -658,7 +656,19 @@ __global__ void __launch_bounds__(256) xattn2_smem_kernel(const uint16_t* __rest
     const int n4 = heads * C / 4;
     const float4* gU = reinterpret_cast<const float4*>(U);
     const float4* gM = reinterpret_cast<const float4*>(M);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    // four loads of each matrix in flight per thread (one per iteration left the 205 KB fill of C = 1280 latency-bound: 25 us)
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = __ldg(gU + i + k * blockDim.x); b[k] = __ldg(gM + i + k * blockDim.x); }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        reinterpret_cast<float4*>(sU)[i + k * blockDim.x] = a[k];
+        reinterpret_cast<float4*>(sM)[i + k * blockDim.x] = b[k];
+      }
+    }
+    for (; i < n4; i += blockDim.x) {
       reinterpret_cast<float4*>(sU)[i] = __ldg(gU + i);
       reinterpret_cast<float4*>(sM)[i] = __ldg(gM + i);
     }
@@ -1017,17 +1027,13 @@ cudaError_t layernorm(const void* x, void* y, long long tokens, int C, const flo
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   uint16_t* yo = reinterpret_cast<uint16_t*>(y);
   const int kv = (C / 8 + 31) / 32;
-  static const bool ln_tok2 = [] { const char* v = getenv("GP_LN_TOK"); return v && v[0] == '2'; }();   // A/B switch
-  const int tok = (ln_tok2 && kv <= 3) ? 2 : 1;
+  // one token per warp; two per warp (all loads up front) measured slower: 80 registers, 0.87 -> 1.08 ms per step (r2m)
+  const int tok = 1;
   const long long blocks = (tokens + tpb * tok - 1) / (tpb * tok);
-  if (tok == 1 && kv <= 2)
+  if (kv <= 2)
     GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 2, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
-  else if (tok == 1 && kv <= 3)
-    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 3, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
-  else if (kv <= 2)
-    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 2, 2>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   else if (kv <= 3)
-    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 3, 2>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
+    GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 3, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   else
     GP_DISPATCH_BF16(bf16, (launch(layernorm_kernel<BF, 5, 1>, (unsigned)blocks, tpb * 32, 0, s, xi, yo, tokens, C, gamma, beta, eps, lo)));
   return cudaGetLastError();
@@ -1114,7 +1120,9 @@ cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, c
     if (per_sm > 2) per_sm = 2;                       // 256 threads at <= 128 registers
     if (per_sm < 1) per_sm = 1;
     const int tok = kv <= 3 ? 2 : 1;
-    long long grid = (tokens + 8 * tok - 1) / (8 * tok);
+    const int threads = kv <= 3 ? 256 : 512;          // C = 1280 leaves room for one CTA per SM: 16 warps instead of 8
+    if (kv > 3) per_sm = 1;
+    long long grid = (tokens + (threads / 32) * tok - 1) / ((threads / 32) * tok);
     if (grid > (long long)sms[dev & 63] * per_sm) grid = (long long)sms[dev & 63] * per_sm;
     const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
     uint16_t* yo = reinterpret_cast<uint16_t*>(y);
@@ -1123,7 +1131,7 @@ cudaError_t xattn2(const void* x, void* y, long long tokens, int C, int heads, c
     else if (kv <= 3)
       GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 3, 2>, (unsigned)grid, 256, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
     else
-      GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 5, 1>, (unsigned)grid, 256, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
+      GP_DISPATCH_BF16(bf16, (launch(xattn2_smem_kernel<BF, 5, 1>, (unsigned)grid, threads, smem, s, xi, yo, tokens, C, heads, U, u0, M, c0, eps, lo)));
     return cudaGetLastError();
   }
   if (kv <= 2)
