@@ -132,6 +132,32 @@ static int choose_bn(int cout, int force) {
   const int n = ceil_div(cout, 256);
   return ceil_div(ceil_div(cout, n), 16) * 16;
 }
+// Wave-aware N tile for the small maps (the UNet's deep levels at any batch, everything at batch 1): the persistent grid
+// runs ceil(tiles / SMs) waves of tiles whose duration scales with the MMA width, so a 12x12x8 level (9 M tiles) with
+// BN = 256 keeps 45 of 148 SMs busy for one long wave where BN = 64 runs 180 short tiles.  Cost model per tile, in
+// units of a 128-wide tile: 256 -> 2, 192 -> 1.5, 128 -> 1, 64 -> 0.75 (a 128 x 64 x 16 MMA is bound by its 6 KB of
+// operand fetch, 48 cycles, not by its 32 tensor cycles).  Ties keep the wider tile (fewer re-reads of the A operand),
+// which leaves every layer with more than a few waves where choose_bn put it.  GP_BN_WAVES=0: off (A/B switch).
+static int choose_bn_waves(int cout, long long work_px, int num_sms, int bn_default) {
+  static const bool off = [] { const char* e = std::getenv("GP_BN_WAVES"); return e && e[0] == '0'; }();
+  if (off || cout % 64 != 0 || cout < 128) return bn_default;
+  auto cost = [&](int bn) {
+    const int mt = (bn <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+    const long long mtiles = (work_px + 128 * mt - 1) / (128 * mt);
+    const long long tiles = mtiles * ceil_div(cout, bn);
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const double per_tile = bn == 64 ? 0.75 : bn / 128.0;
+    return (double)waves * mt * per_tile;
+  };
+  int best = bn_default;
+  double best_cost = cost(bn_default);
+  for (int bn : {256, 192, 128, 64}) {
+    if (bn >= bn_default) continue;                    // only ever narrower than the default
+    const double c = cost(bn);
+    if (c < best_cost * 0.97) { best_cost = c; best = bn; }
+  }
+  return best;
+}
 // pick the TW x TH = `rows` (128 or 256) patch with the least padding waste (ties: wider rows)
 static void choose_tile(int gw, int gh, int rows, int* tw, int* th, int* shift) {
   double best = 1e30;
@@ -207,9 +233,10 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   if (!a.out_f32) GP_REQUIRE(a.out.N == N && a.out.H == Ho && a.out.W == Wo, name + ": output shape mismatch");
   // GroupNorm partial sums from the epilogue: same decision (and arena allocation) in both passes
   const bool tokens_mode = (a.ks == 1 && a.mode == 0 && a.sc.empty() && a.srcs.size() == 1 && !a.out_f32);
-  const int bn_pre = choose_bn(Cout, a.force_bn);
   const long long work_px = tokens_mode ? (long long)N * H * W
                                         : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
+  int bn_pre = choose_bn(Cout, a.force_bn);
+  if (!a.force_bn && !(a.flags & IG_GEGLU) && !gn_fused) bn_pre = choose_bn_waves(Cout, work_px, num_sms, bn_pre);
   const int mt_pre = gn_fused ? ((bn_pre <= 128 && (H % 2) == 0) ? 2 : 1) : (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
@@ -240,7 +267,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   p.res2 = a.res2 ? ptr(*a.res2) : nullptr;
   p.out = a.out_f32 ? (void*)a.out_f32 : ptr(a.out);
   p.Cout = Cout;
-  p.BN = choose_bn(Cout, a.force_bn);
+  p.BN = bn_pre;
   p.Z1 = 1; p.Z0 = 1;
   p.out_sy = p.out_sx = 1;
   const bool tokens = tokens_mode;
