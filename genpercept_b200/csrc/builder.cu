@@ -1,6 +1,7 @@
 // Plan-time arena and op-list builder: turns layer-level calls (conv, attention, norms ...) into
 // fully parameterised kernel launches (tensor maps encoded once, at plan time).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include <cstdlib>
@@ -132,32 +133,6 @@ static int choose_bn(int cout, int force) {
   const int n = ceil_div(cout, 256);
   return ceil_div(ceil_div(cout, n), 16) * 16;
 }
-// Wave-aware N tile for the small maps (the UNet's deep levels at any batch, everything at batch 1): the persistent grid
-// runs ceil(tiles / SMs) waves of tiles whose duration scales with the MMA width, so a 12x12x8 level (9 M tiles) with
-// BN = 256 keeps 45 of 148 SMs busy for one long wave where BN = 64 runs 180 short tiles.  Cost model per tile, in
-// units of a 128-wide tile: 256 -> 2, 192 -> 1.5, 128 -> 1, 64 -> 0.75 (a 128 x 64 x 16 MMA is bound by its 6 KB of
-// operand fetch, 48 cycles, not by its 32 tensor cycles).  Ties keep the wider tile (fewer re-reads of the A operand),
-// which leaves every layer with more than a few waves where choose_bn put it.  GP_BN_WAVES=0: off (A/B switch).
-static int choose_bn_waves(int cout, long long work_px, int num_sms, int bn_default) {
-  static const bool off = [] { const char* e = std::getenv("GP_BN_WAVES"); return e && e[0] == '0'; }();
-  if (off || cout % 64 != 0 || cout < 128) return bn_default;
-  auto cost = [&](int bn) {
-    const int mt = (bn <= 128 && work_px >= 256LL * 148) ? 2 : 1;
-    const long long mtiles = (work_px + 128 * mt - 1) / (128 * mt);
-    const long long tiles = mtiles * ceil_div(cout, bn);
-    const long long waves = (tiles + num_sms - 1) / num_sms;
-    const double per_tile = bn == 64 ? 0.75 : bn / 128.0;
-    return (double)waves * mt * per_tile;
-  };
-  int best = bn_default;
-  double best_cost = cost(bn_default);
-  for (int bn : {256, 192, 128, 64}) {
-    if (bn >= bn_default) continue;                    // only ever narrower than the default
-    const double c = cost(bn);
-    if (c < best_cost * 0.97) { best_cost = c; best = bn; }
-  }
-  return best;
-}
 // pick the TW x TH = `rows` (128 or 256) patch with the least padding waste (ties: wider rows)
 static void choose_tile(int gw, int gh, int rows, int* tw, int* th, int* shift) {
   double best = 1e30;
@@ -169,6 +144,38 @@ static void choose_tile(int gw, int gh, int rows, int* tw, int* th, int* shift) 
   }
 }
 
+// Tile shape (BN, MT) for the layers that do not fill the GPU (the UNet's deep levels at any batch, everything at batch
+// 1).  Two bounds per candidate: the tensor time of the longest-running SM — ceil(tiles / SMs) waves of tiles whose
+// duration scales with the MMA width (a 128 x 64 x 16 MMA is bound by its 6 KB of operand fetch: 48 cycles, not 32) — and
+// the L2 -> SM operand traffic, tiles x K x (128 MT + BN) x 2 bytes at the ~5.2 TB/s these layers sustain (r2n: the
+// 2560 -> 1280 conv on 8 x 12 x 12 pixels moves 796 MB with BN = 256 and 1062 MB with BN = 128: 152 vs 210 us, although
+// BN = 128 doubles the number of busy SMs; at batch 1 the same level has 2 M tiles, BN = 256 keeps 10 SMs busy for 61 us
+// and BN = 64 runs 40 tiles in ~25 us).  A candidate replaces the default only for a predicted gain above 10 %, so
+// every layer with many waves stays where choose_bn put it.  GP_TILE_MODEL=0: off (A/B switch).
+struct TileShape { int bn, mt; };
+template <class MTilesFn>
+static TileShape choose_tile_shape(int cout, double k_elems, int num_sms, TileShape dflt, MTilesFn mtiles_of) {
+  static const bool off = [] { const char* e = std::getenv("GP_TILE_MODEL"); return e && e[0] == '0'; }();
+  if (off || cout % 64 != 0 || cout < 128) return dflt;
+  auto cost = [&](TileShape t) {
+    const double tiles = (double)mtiles_of(t.mt) * ceil_div(cout, t.bn);
+    const double waves = std::ceil(tiles / num_sms);
+    const double cyc_per_kb = 4.0 * t.mt * (t.bn == 64 ? 48.0 : t.bn / 2.0);
+    const double t_mma = waves * ((k_elems / 64.0) * cyc_per_kb / 1.5e9 + 3e-6);     // + epilogue / pipeline fill per wave
+    const double t_l2 = tiles * k_elems * (128.0 * t.mt + t.bn) * 2.0 / 5.2e12;
+    return std::max(t_mma, t_l2);
+  };
+  TileShape best = dflt;
+  const double c0 = cost(dflt);
+  double best_cost = c0;
+  for (int bn : {256, 192, 128, 64})
+    for (int mt : {1, 2}) {
+      if (mt == 2 && bn > 128) continue;
+      const double c = cost(TileShape{bn, mt});
+      if (c < 0.9 * c0 && c < best_cost) { best_cost = c; best = TileShape{bn, mt}; }
+    }
+  return best;
+}
 static void check_cuda(cudaError_t e, const std::string& what) {
   if (e != cudaSuccess) throw GpError(GP_ERR_CUDA, what + ": " + cudaGetErrorString(e));
 }
@@ -236,8 +243,20 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   const long long work_px = tokens_mode ? (long long)N * H * W
                                         : (long long)(a.mode == 3 ? W : Wo) * (a.mode == 3 ? H : Ho) * N * (a.mode == 3 ? 4 : 1);
   int bn_pre = choose_bn(Cout, a.force_bn);
-  if (!a.force_bn && !(a.flags & IG_GEGLU) && !gn_fused) bn_pre = choose_bn_waves(Cout, work_px, num_sms, bn_pre);
-  const int mt_pre = gn_fused ? ((bn_pre <= 128 && (H % 2) == 0) ? 2 : 1) : (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+  int mt_pre = gn_fused ? ((bn_pre <= 128 && (H % 2) == 0) ? 2 : 1) : (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+  if (!a.force_bn && !(a.flags & IG_GEGLU) && !gn_fused) {
+    const int gw = (a.mode == 3) ? W : Wo, gh = (a.mode == 3) ? H : Ho;
+    auto mtiles_of = [&](int mt) -> long long {
+      if (tokens_mode) return (work_px + 128 * mt - 1) / (128 * mt);
+      int tw = 128, th = mt, sh = 7;
+      choose_tile(gw, gh, 128 * mt, &tw, &th, &sh);
+      return (long long)N * (a.mode == 3 ? 4 : 1) * ceil_div(gw, tw) * ceil_div(gh, th);
+    };
+    const double k_elems = flops / (2.0 * N * Ho * Wo * (double)Cout) * (a.mode == 3 ? 4.0 / 9.0 : 1.0);
+    const TileShape ts = choose_tile_shape(Cout, k_elems, num_sms, TileShape{bn_pre, mt_pre}, mtiles_of);
+    bn_pre = ts.bn;
+    mt_pre = ts.mt;
+  }
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&
                       (is_geglu ? (std::getenv("GP_STAGED_GEGLU") != nullptr && !split_ &&   // measured slower than the direct GEGLU stores (r1g)
@@ -275,7 +294,7 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
     const long long ntok = (long long)N * H * W;
     GP_REQUIRE(ntok < (1LL << 31), name + ": too many tokens");
     p.gridW = (int)ntok; p.gridH = 1;
-    p.MT = (p.BN <= 128 && ntok >= 256 * 148) ? 2 : 1;
+    p.MT = mt_pre;
     p.TW = 128 * p.MT; p.TH = 1; p.tw_shift = p.MT == 2 ? 8 : 7;
     p.nseg[0] = 1;
     p.seg[0][0] = IgemmSeg{0, 0, 0, (uint16_t)ceil_div(s0.C, 64)};
