@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
   uint64_t* res_bar = tempty_bar + 2;                                  // [epilogue warps] residual tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
   float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
-  float* sacc = sbias + kBiasSlots;   // [4 epilogue warps][Cout][2], only with p.stats
+  float* sacc = sbias + p.bias_slots;   // [4 epilogue warps][Cout][2], only with p.stats
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp < kEpiWarps && p.tma_store) {
-    epilogue_staged<BF16, kEpiWarps>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    run_epilogue_staged<BF16, kEpiWarps, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
   } else if (warp < kEpiWarps) {
     epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   }
@@ -286,14 +286,22 @@ const char* igemm_finalize(IgemmParams* p) {
   // staging: one 4 KiB tile per epilogue warp (8; 4 in the patch kernel's GroupNorm-transform build), x2 for the (hi, lo) layout
   const int epi_warps = (p->patch && p->gn_ss) ? 4 : 8;
   const int staging = p->tma_store ? epi_warps * 4096 * (p->out_lo ? 2 : 1) : 0;
-  int st = (kMaxSmem - 3072 - stats_bytes - staging) / stage_bytes;
+  // bias: one N tile (288 floats, inside the 3072 reserved bytes) or the whole padded vector when it is small (<= 16 KiB)
+  p->bias_slots = kBiasSlots;
+  p->bias_all = 0;
+  if (p->n_tiles_n > 1 && p->n_tiles_n * p->BN + 32 <= 4096 && getenv("GP_NO_BIAS_ALL") == nullptr) {
+    p->bias_all = 1;
+    p->bias_slots = p->n_tiles_n * p->BN + 32;
+  }
+  const int bias_extra = (p->bias_slots - kBiasSlots) * (int)sizeof(float);
+  int st = (kMaxSmem - 3072 - stats_bytes - staging - bias_extra) / stage_bytes;
   if (p->patch) {
     if (p->TW != 128 || p->TH != p->MT || p->Z0 != 1 || p->Z1 < 1 || p->nseg[0] != 9 + (p->kc_sc > 0 ? 1 : 0) || p->kc_count < 1 ||
         p->nkb[0] != 9 * p->kc_count + p->kc_sc || p->npass != 1 || p->gridW % 128 || p->gridH % p->TH)
       return "patch mode needs TW = 128, TH = MT, full tiles and a single-source 3x3 tap table (+ shortcut chunks)";
     if (p->gn_ss && p->gn_C != p->kc_count * 64) return "patch mode: GroupNorm channels must equal the source's";
     p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
-    st = (kMaxSmem - 3072 - stats_bytes - staging - 2 * p->a_slot_bytes) / (p->BN * 128);
+    st = (kMaxSmem - 3072 - stats_bytes - staging - bias_extra - 2 * p->a_slot_bytes) / (p->BN * 128);
     if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
       const int v = atoi(env);
       if (v >= 2 && v < st) st = v;

@@ -92,6 +92,9 @@ struct IgemmParams {
   // staging tile before the accumulator is read.  Row-per-thread global loads of a residual cost 32 L1 sector
   // look-ups per warp request (ncu r1k: 58 % tensor pipe with a residual vs 92 % without, same layer).
   int res_tma;
+  int bias_slots;                // floats of shared memory holding the bias: 288 (one N tile, reloaded per tile) or, when the
+                                 // layer has several N tiles and Cout is small enough, all of them (loaded once: bias_all)
+  int bias_all;
   int res_prefetch;              // L2-prefetch the next tile's residual boxes one tile period ahead (GP_NO_RES_PREFETCH=1: off)
   CUtensorMap tmRes[kMaxClasses];
   // Patch-resident main loop (igemm_patch.cu; 3x3 stride-1, one source, TW = 128, TH = MT = 1 or 2): per

@@ -112,10 +112,14 @@ __device__ __forceinline__ void epi_sync() {   // the epilogue threads only
 // memory those miss to L2 (~600 cycles), in front of every piece (ncu r2: the K = 1 stem GEMM, nothing but epilogue, ran
 // with the epilogue warps issuing 22 % of the time and no unit above 25 %).
 constexpr int kBiasSlots = 288;
+// A layer with several N tiles changes tile column on every tile of a CTA (tiles are numbered N-fastest and taken with a
+// stride of gridDim.x), i.e. two barriers of all epilogue warps plus an L2 round trip per tile: when the padded Cout fits
+// (p.bias_all, igemm_finalize) the whole bias vector is loaded once instead.
 template <int NW>
 __device__ __forceinline__ void load_bias_tile(const IgemmParams& p, float* sbias, int n_base, int etid) {
   epi_sync<NW>();                              // nobody still reads the previous tile's values
-  for (int i = etid; i < kBiasSlots; i += NW * 32) {
+  const int count = p.bias_all ? p.bias_slots : kBiasSlots;
+  for (int i = etid; i < count; i += NW * 32) {
     const int n = n_base + i;
     sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
   }
@@ -132,7 +136,10 @@ __device__ __forceinline__ void bias32(const float* sbias, int c, float (&bz)[32
 // Staged epilogue (shared by the tap-streaming and the patch-resident main loops): TMEM -> registers
 // (bias / residuals / ReLU) -> 16-bit rows in a SWIZZLE_128B shared tile -> one TMA store per
 // (warp, 64-channel group), plus the GroupNorm partial sums read back column-wise from the tile.
-template <bool BF16, int NW>
+// SPLIT / RES / GEGLU are compile-time: with run-time flags one 32 x 64 piece executed ~830 warp instructions, 97 of them MOVs
+// and 27 branches around the variants not taken (ncu source page, r2q: the 320 -> 2560 linear issues 13.4 k warp
+// instructions per 128 x 256 tile against 2560 tensor cycles).  RES: 0 none, 1 residual tile through TMA, 2 per-thread rows.
+template <bool BF16, int NW, bool SPLIT, int RES, bool GEGLU>
 __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, float* sbias, uint64_t* tfull_bar,
                                                 uint64_t* tempty_bar, uint64_t* res_bar, uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue, staged + TMA store
@@ -145,18 +152,18 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   uint8_t* stg = stg_base + warp * 4096;
   const uint32_t stg_addr = smem_u32(stg);
   const uint32_t my_row = stg_addr + lane * 128;
-  const bool split = p.out_lo != 0;          // high-precision mode: a second staged tile (+NW * 4 KiB) takes the lo plane
+  constexpr bool split = SPLIT;              // high-precision mode: a second staged tile (+NW * 4 KiB) takes the lo plane
   const uint32_t my_row_lo = my_row + NW * 4096;
   // 64-channel groups (128 GEMM columns with GEGLU) of the N tile go to the two halves by parity; a tile with one group only
   // is done by half 0 (statistics: the halves then never accumulate the same channel into sacc[wq])
-  const int gshift = (p.flags & IG_GEGLU) ? 7 : 6;
+  constexpr int gshift = GEGLU ? 7 : 6;
   const bool two_groups = NW == 8 && (p.BN >> gshift) >= 2;
   auto mine = [&](int c0) { return NW == 4 || (two_groups ? ((c0 >> gshift) & 1) == half : half == 0); };
   const int sw = lane & 7;
   int acc = 0;
   uint32_t acc_phase = 0, res_phase = 0;
   const bool relu = (p.flags & IG_RELU) != 0;
-  const bool geglu = (p.flags & IG_GEGLU) != 0;
+  constexpr bool geglu = GEGLU;
   const bool do_stats = p.stats != nullptr;
   const int etid = threadIdx.x;
   int cur_img = -1;
@@ -175,20 +182,22 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
     for (int i = etid; i < 8 * p.Cout; i += NW * 32) sacc[i] = 0.f;
     epi_sync<NW>();
   }
+  if (p.bias_all) load_bias_tile<NW>(p, sbias, 0, etid);
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
     const int cls = p.cls_from_z0 ? t.z0 : 0;
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
-    if (t.n_tile != cur_nt) {
+    if (t.n_tile != cur_nt && !p.bias_all) {
       load_bias_tile<NW>(p, sbias, n_base, etid);
       cur_nt = t.n_tile;
     }
+    const int bias_origin = p.bias_all ? 0 : n_base;
     // The residual boxes of this CTA's NEXT tile are pulled into L2 now, a whole tile period before their TMA loads:
     // those loads sit serially in front of every 32 x 64 piece of the epilogue, and with DRAM latency (1.5 us under
     // load) four of them per warp outlast the main loop of the short-K (Cout = 128) layers (r2: residual convs 20-30 %
     // slower than plain ones; the main loop of a 128->128 tile is 6 us).
-    if (p.res_prefetch && lane == 0 && tile + (int)gridDim.x < p.total_tiles) {
+    if (RES == 1 && p.res_prefetch && lane == 0 && tile + (int)gridDim.x < p.total_tiles) {
       const TileCoord tn = decode_tile(p, tile + gridDim.x);
       const int ncls = p.cls_from_z0 ? tn.z0 : 0;
       for (int h = 0; h < p.MT; ++h) {
@@ -219,7 +228,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
         const int n0 = n_base + c0;
         if (n0 >= p.Cout) break;
         if (!mine(c0)) continue;
-        if (geglu) {   // 128 GEMM columns = 4 x [16 values | 16 gates] -> 64 outputs = one staged 128-byte row
+        if constexpr (geglu) {   // 128 GEMM columns = 4 x [16 values | 16 gates] -> 64 outputs = one staged 128-byte row
           if (c0 & 64) continue;
           if (lane == 0) tma_store_wait_read0();
           __syncwarp();
@@ -227,7 +236,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           for (int sub = 0; sub < 4; ++sub) {
             const int ns = n0 + sub * 32;
             float bz[32];
-            bias32(sbias, ns - n_base, bz);
+            bias32(sbias, ns - bias_origin, bz);
             if (!waited) {
               mbar_wait(&tfull_bar[acc], acc_phase, 4);
               tc_fence_after();
@@ -258,11 +267,11 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
             tma_store_commit();
           }
           continue;
-        }
+        } else {
         if (lane == 0) tma_store_wait_read0();                // the previous store has finished reading the tile
         __syncwarp();
         uint4 rt[8];                                          // this thread's residual row (64 channels), res_tma only
-        if (p.res_tma) {
+        if constexpr (RES == 1) {
           if (lane == 0) {
             mbar_expect_tx(&res_bar[warp], 4096);
             tma_load_4d(stg, &p.tmRes[cls], &res_bar[warp], n0, sx, sy, t.z1);
@@ -282,10 +291,10 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           const int ns = n0 + sub * 32;
           const long long off = pix_off + ns;
           float bz[32];
-          bias32(sbias, ns - n_base, bz);
+          bias32(sbias, ns - bias_origin, bz);
           uint4 r1[4], r2[4];
-          const bool has1 = valid && p.res1 != nullptr, has2 = valid && p.res2 != nullptr;
-          if (p.res_tma) {
+          const bool has1 = RES == 1 || (RES == 2 && valid && p.res1 != nullptr), has2 = RES == 2 && valid && p.res2 != nullptr;
+          if constexpr (RES == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) r1[q] = rt[sub * 4 + q];
           } else if (has1) {
@@ -376,6 +385,7 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
           float* d = sacc + ((size_t)wq * p.Cout + n0 + 2 * lane) * 2;
           d[0] += s0; d[1] += q0; d[2] += s1; d[3] += q1;
         }
+        }   // !GEGLU
       }
     }
     if (!waited) {
@@ -391,6 +401,27 @@ __device__ __forceinline__ void epilogue_staged(const IgemmParams& p, uint8_t* s
   if (do_stats && cur_img >= 0) flush_stats(cur_img);
 }
 
+
+// Run-time flags -> the specialised staged epilogue.  LEAN (the patch-resident kernel): no (hi, lo) layout, no GEGLU.
+template <bool BF16, int NW, bool LEAN>
+__device__ __forceinline__ void run_epilogue_staged(const IgemmParams& p, uint8_t* stg_base, float* sacc, float* sbias, uint64_t* tfull_bar,
+                                                    uint64_t* tempty_bar, uint64_t* res_bar, uint32_t tmem_base, int warp, int lane) {
+  const int rm = p.res_tma ? 1 : ((p.res1 != nullptr || p.res2 != nullptr) ? 2 : 0);
+  if constexpr (!LEAN) {
+    if (p.flags & IG_GEGLU) {
+      epilogue_staged<BF16, NW, false, 0, true>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+      return;
+    }
+    if (p.out_lo != 0) {
+      if (rm == 2) epilogue_staged<BF16, NW, true, 2, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+      else epilogue_staged<BF16, NW, true, 0, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+      return;
+    }
+  }
+  if (rm == 1) epilogue_staged<BF16, NW, false, 1, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+  else if (rm == 2) epilogue_staged<BF16, NW, false, 2, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+  else epilogue_staged<BF16, NW, false, 0, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+}
 
 // Direct epilogue: TMEM -> registers (bias / residuals / ReLU / affine clamp / GEGLU) -> global stores straight from
 // the registers: fp32 NCHW maps, odd channel counts, GEGLU, the high-precision (hi, lo) layout.
@@ -426,15 +457,17 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
     for (int i = etid; i < 8 * p.Cout; i += NW * 32) sacc[i] = 0.f;
     epi_sync<NW>();
   }
+  if (p.bias_all) load_bias_tile<NW>(p, sbias, 0, etid);
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
     const int cls = p.cls_from_z0 ? t.z0 : 0;
     const int n_base = t.n_tile * p.BN;
     bool waited = false;
-    if (t.n_tile != cur_nt) {
+    if (t.n_tile != cur_nt && !p.bias_all) {
       load_bias_tile<NW>(p, sbias, n_base, etid);
       cur_nt = t.n_tile;
     }
+    const int bias_origin = p.bias_all ? 0 : n_base;
     if (do_stats) {
       const int img = p.stats_hw ? (t.tx * p.TW) / p.stats_hw : t.z1;
       if (img != cur_img) {
@@ -461,7 +494,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
         const bool vec = !f32out && live && (nvalid == ncols) && ((off & 7) == 0);
         // operands that do not depend on the accumulator are fetched BEFORE waiting on it
         float bz[32];
-        bias32(sbias, c0, bz);
+        bias32(sbias, n_base - bias_origin + c0, bz);
         uint4 r1[4], r2[4];
         const bool has1 = vec && p.res1 != nullptr, has2 = vec && p.res2 != nullptr;
         if (has1) {

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
   uint64_t* res_bar = tempty_bar + 2;                                  // [epilogue warps] residual tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
   float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [kBiasSlots]
-  float* sacc = sbias + kBiasSlots;
+  float* sacc = sbias + p.bias_slots;
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
   if (warp < NE) {
     // ===================================================================== epilogue
     if constexpr (XFORM) setmaxnreg_inc<232>();
-    if (p.tma_store) epilogue_staged<BF16, NE>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    if (p.tma_store) run_epilogue_staged<BF16, NE, true>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
     else epilogue_direct<BF16, NE>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   } else if (rw < 4) {
     if constexpr (XFORM) setmaxnreg_dec<72>();
