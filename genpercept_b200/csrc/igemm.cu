@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
   } else if (warp < kEpiWarps && p.tma_store) {
     run_epilogue_staged<BF16, kEpiWarps, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
   } else if (warp < kEpiWarps) {
-    epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    run_epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -293,8 +293,16 @@ const char* igemm_finalize(IgemmParams* p) {
     p->bias_all = 1;
     p->bias_slots = p->n_tiles_n * p->BN + 32;
   }
-  const int bias_extra = (p->bias_slots - kBiasSlots) * (int)sizeof(float);
+  int bias_extra = (p->bias_slots - kBiasSlots) * (int)sizeof(float);
   int st = (kMaxSmem - 3072 - stats_bytes - staging - bias_extra) / stage_bytes;
+  // ... but never at the price of a pipeline stage: the BN = 256 layers fit exactly four 48 KiB stages, and the UNet's deep
+  // levels (L2-latency-bound) lost 25-30 % with three (r2r: 2560 -> 1280 on 8 x 12 x 12 pixels 134 -> 179 us)
+  if (p->bias_all && !p->patch && st < (kMaxSmem - 3072 - stats_bytes - staging) / stage_bytes) {
+    p->bias_all = 0;
+    p->bias_slots = kBiasSlots;
+    bias_extra = 0;
+    st = (kMaxSmem - 3072 - stats_bytes - staging) / stage_bytes;
+  }
   if (p->patch) {
     if (p->TW != 128 || p->TH != p->MT || p->Z0 != 1 || p->Z1 < 1 || p->nseg[0] != 9 + (p->kc_sc > 0 ? 1 : 0) || p->kc_count < 1 ||
         p->nkb[0] != 9 * p->kc_count + p->kc_sc || p->npass != 1 || p->gridW % 128 || p->gridH % p->TH)
@@ -302,6 +310,11 @@ const char* igemm_finalize(IgemmParams* p) {
     if (p->gn_ss && p->gn_C != p->kc_count * 64) return "patch mode: GroupNorm channels must equal the source's";
     p->a_slot_bytes = ((p->TW + 2) * (p->TH + 2) * 128 + 1023) & ~1023;
     st = (kMaxSmem - 3072 - stats_bytes - staging - bias_extra - 2 * p->a_slot_bytes) / (p->BN * 128);
+    if (p->bias_all && st < (kMaxSmem - 3072 - stats_bytes - staging - 2 * p->a_slot_bytes) / (p->BN * 128)) {
+      p->bias_all = 0;
+      p->bias_slots = kBiasSlots;
+      st = (kMaxSmem - 3072 - stats_bytes - staging - 2 * p->a_slot_bytes) / (p->BN * 128);
+    }
     if (const char* env = getenv("GP_PATCH_STAGES")) {          // experiment: depth of the weight ring
       const int v = atoi(env);
       if (v >= 2 && v < st) st = v;

@@ -425,7 +425,9 @@ __device__ __forceinline__ void run_epilogue_staged(const IgemmParams& p, uint8_
 
 // Direct epilogue: TMEM -> registers (bias / residuals / ReLU / affine clamp / GEGLU) -> global stores straight from
 // the registers: fp32 NCHW maps, odd channel counts, GEGLU, the high-precision (hi, lo) layout.
-template <bool BF16, int NW>
+// LEAN = the GEGLU projection of the default mode (full 32-column chunks, no residual, 16-bit output, no (hi, lo) planes): every
+// other variant is compiled out of its loop (same reasoning as the staged epilogue's template parameters).
+template <bool BF16, int NW, bool LEAN>
 __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sacc, float* sbias, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                 uint32_t tmem_base, int warp, int lane) {
   // ===================================================================== epilogue
@@ -434,10 +436,13 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
   const bool two_chunks = NW == 8 && p.BN > 32;
   int acc = 0;
   uint32_t acc_phase = 0;
-  const bool f32out = (p.flags & IG_OUT_F32_NCHW) != 0;
-  const bool relu = (p.flags & IG_RELU) != 0;
-  const bool aff = (p.flags & IG_AFFINE_CLAMP01) != 0;
-  const bool geglu = (p.flags & IG_GEGLU) != 0;
+  const bool f32out = !LEAN && (p.flags & IG_OUT_F32_NCHW) != 0;
+  const bool relu = !LEAN && (p.flags & IG_RELU) != 0;
+  const bool aff = !LEAN && (p.flags & IG_AFFINE_CLAMP01) != 0;
+  const bool geglu = LEAN || (p.flags & IG_GEGLU) != 0;
+  const void* const res1 = LEAN ? nullptr : p.res1;
+  const void* const res2 = LEAN ? nullptr : p.res2;
+  const long long out_lo = LEAN ? 0 : p.out_lo;
   const bool do_stats = false;               // statistics are produced by the staged (TMA store) epilogue only
   const int etid = threadIdx.x;              // 0..127 among the epilogue threads
   int cur_img = -1;
@@ -486,9 +491,9 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride + h * 128;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         if (NW == 8 && (two_chunks ? ((c0 >> 5) & 1) != half : half != 0)) continue;
-        const int ncols = (p.BN - c0 >= 32) ? 32 : 16;
+        const int ncols = (LEAN || p.BN - c0 >= 32) ? 32 : 16;
         const int n0 = n_base + c0;
-        const int nvalid = min(ncols, p.Cout - n0);
+        const int nvalid = LEAN ? 32 : min(ncols, p.Cout - n0);
         const bool live = valid && nvalid > 0;
         const long long off = pix_off + n0;
         const bool vec = !f32out && live && (nvalid == ncols) && ((off & 7) == 0);
@@ -496,14 +501,14 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
         float bz[32];
         bias32(sbias, n_base - bias_origin + c0, bz);
         uint4 r1[4], r2[4];
-        const bool has1 = vec && p.res1 != nullptr, has2 = vec && p.res2 != nullptr;
+        const bool has1 = vec && res1 != nullptr, has2 = vec && res2 != nullptr;
         if (has1) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + off);
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(res1) + off);
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q * 8 < ncols) r1[q] = rp[q];
         }
         if (has2) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + off);
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(res2) + off);
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q * 8 < ncols) r2[q] = rp[q];
         }
@@ -513,7 +518,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
           waited = true;
         }
         uint32_t r[32];
-        if (ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
+        if (LEAN || ncols == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
         tmem_ld_wait();
         if (!live) continue;
         float v[32];
@@ -535,25 +540,25 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
         if (has1) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r1[q]);
-        } else if (p.res1 != nullptr && live) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res1) + off;
+        } else if (res1 != nullptr && live) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(res1) + off;
 #pragma unroll
           for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
         }
         if (has2) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], r2[q]);
-        } else if (p.res2 != nullptr && live) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res2) + off;
+        } else if (res2 != nullptr && live) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(res2) + off;
 #pragma unroll
           for (int q = 0; q < 32; ++q) if (q < nvalid) v[q] += cvt16<BF16>(rp[q]);
         }
-        if (p.out_lo) {      // high-precision layout: lo planes of the residuals
+        if (out_lo) {      // high-precision layout: lo planes of the residuals
 #pragma unroll
           for (int ri = 0; ri < 2; ++ri) {
-            const void* rb = ri == 0 ? p.res1 : p.res2;
+            const void* rb = ri == 0 ? res1 : res2;
             if (rb == nullptr || !live) continue;
-            const uint16_t* rp = reinterpret_cast<const uint16_t*>(rb) + off + p.out_lo;
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(rb) + off + out_lo;
             if (vec) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) if (q * 8 < ncols) add8<BF16>(&v[q * 8], reinterpret_cast<const uint4*>(rp)[q]);
@@ -573,14 +578,14 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
 #pragma unroll
           for (int q = 0; q < 16; ++q) g[q] = v[q] * gelu_erf(v[16 + q]);
 #pragma unroll
-          for (int q = 0; q < 16; q += 8) store8_hl<BF16>(og + q, p.out_lo, &g[q]);
+          for (int q = 0; q < 16; q += 8) store8_hl<BF16>(og + q, out_lo, &g[q]);
           continue;
         }
         uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + off;
         if (vec) {
 #pragma unroll
           for (int q = 0; q < 32; q += 8) {
-            if (q < ncols) store8_hl<BF16>(op + q, p.out_lo, &v[q]);
+            if (q < ncols) store8_hl<BF16>(op + q, out_lo, &v[q]);
           }
         } else if (live) {
 #pragma unroll
@@ -588,7 +593,7 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
             if (q < nvalid) {
               const uint16_t h = (uint16_t)(pack16<BF16>(v[q], 0.f) & 0xFFFF);
               op[q] = h;
-              if (p.out_lo) op[q + p.out_lo] = (uint16_t)(pack16<BF16>(v[q] - cvt16<BF16>(h), 0.f) & 0xFFFF);
+              if (out_lo) op[q + out_lo] = (uint16_t)(pack16<BF16>(v[q] - cvt16<BF16>(h), 0.f) & 0xFFFF);
             }
           }
         }
@@ -604,6 +609,15 @@ __device__ __forceinline__ void epilogue_direct(const IgemmParams& p, float* sac
     if (acc == 0) acc_phase ^= 1;
   }
   if (do_stats && cur_img >= 0) flush_stats(cur_img);
+}
+
+template <bool BF16, int NW>
+__device__ __forceinline__ void run_epilogue_direct(const IgemmParams& p, float* sacc, float* sbias, uint64_t* tfull_bar,
+                                                    uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane) {
+  const bool lean = (p.flags & IG_GEGLU) && !(p.flags & (IG_OUT_F32_NCHW | IG_RELU | IG_AFFINE_CLAMP01)) && p.out_lo == 0 &&
+                    p.res1 == nullptr && p.res2 == nullptr && (p.BN % 32) == 0 && (p.Cout % p.BN) == 0;
+  if (lean) epilogue_direct<BF16, NW, true>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  else epilogue_direct<BF16, NW, false>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
 }
 
 }  // namespace

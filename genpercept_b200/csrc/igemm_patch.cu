@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __g
     // ===================================================================== epilogue
     if constexpr (XFORM) setmaxnreg_inc<232>();
     if (p.tma_store) run_epilogue_staged<BF16, NE, true>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
-    else epilogue_direct<BF16, NE>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+    else epilogue_direct<BF16, NE, false>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   } else if (rw < 4) {
     if constexpr (XFORM) setmaxnreg_dec<72>();
     if (rw == 0) {
