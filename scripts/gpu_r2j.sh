@@ -13,3 +13,11 @@ echo "ncu launches exit $?"; wc -l gpurun_out/launches.csv
 bash scripts/gpu_matrix.sh
 bash scripts/gpu_step_dram.sh
 bash scripts/gpu_prof.sh
+# the .ncu-rep files (17 launches with --set full + source) exceed gpurun's 64 MiB return limit: summarise on the box, drop them
+mkdir -p gpurun_out/profiles_out
+GP_PROFILES_DIR=gpurun_out/profiles_out python scripts/make_profiles.py r2 > gpurun_out/make_profiles.log 2>&1; tail -n 2 gpurun_out/make_profiles.log | cut -c1-200
+python scripts/ncu_source_summary.py gpurun_out/prof_igemm.ncu-rep 11 5760 > gpurun_out/profiles_out/r2_linear_after_ncu_source.txt 2>&1
+python scripts/ncu_source_summary.py gpurun_out/prof_igemm.ncu-rep 3 0 > gpurun_out/profiles_out/r2_conv128_ncu_source.txt 2>&1
+python scripts/ncu_source_summary.py gpurun_out/prof_fattn.ncu-rep 1 0 > gpurun_out/profiles_out/r2_fattn_ncu_source.txt 2>&1
+rm -f gpurun_out/prof_igemm.ncu-rep gpurun_out/prof_fattn.ncu-rep
+du -sm gpurun_out

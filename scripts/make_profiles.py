@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
-P = os.path.join(ROOT, "profiles")
+P = os.environ.get("GP_PROFILES_DIR") or os.path.join(ROOT, "profiles")   # on the GPU box: a directory under gpurun_out/
 
 
 def cat(n):
