@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
   const int stage_bytes = a_bytes + p.BN * 128;
   const int stages = p.stages;
   uint8_t* stg_base = smem + stages * stage_bytes;                     // one 4 KiB staging tile per epilogue warp (tma_store only)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? (p.out_lo ? 2 : 1) * kEpiWarps * 4096 : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (p.tma_store ? (p.out_lo ? 2 : 1) * p.epi_warps * 4096 : 0));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], p.MT);
-      mbar_init(&tempty_bar[i], kEpiWarps * 32);
+      mbar_init(&tempty_bar[i], p.epi_warps * 32);
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
@@ -176,10 +176,14 @@ __global__ void __launch_bounds__(kTapThreads, 1) igemm_kernel(const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp < kEpiWarps && p.tma_store) {
-    run_epilogue_staged<BF16, kEpiWarps, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
-  } else if (warp < kEpiWarps) {
-    run_epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  } else if (warp < kEpiWarps && p.epi_warps == kEpiWarps) {
+    if (p.tma_store) run_epilogue_staged<BF16, kEpiWarps, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    else run_epilogue_direct<BF16, kEpiWarps>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
+  } else if (warp < 4) {
+    // four epilogue warps (warps 4..7 idle): the long-K BN = 256 layers, where eight 4 KiB staging tiles would cost the fourth
+    // pipeline stage (igemm_finalize) and the epilogue is hidden behind an 18 k-cycle main loop anyway
+    if (p.tma_store) run_epilogue_staged<BF16, 4, false>(p, stg_base, sacc, sbias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    else run_epilogue_direct<BF16, 4>(p, sacc, sbias, tfull_bar, tempty_bar, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -284,8 +288,18 @@ const char* igemm_finalize(IgemmParams* p) {
   if (p->tma_store && (p->flags & IG_GEGLU) && ((p->Cout % 128) || (p->BN % 128))) return "staged GEGLU needs Cout, BN % 128 == 0";
   if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
   // staging: one 4 KiB tile per epilogue warp (8; 4 in the patch kernel's GroupNorm-transform build), x2 for the (hi, lo) layout
-  const int epi_warps = (p->patch && p->gn_ss) ? 4 : 8;
-  const int staging = p->tma_store ? epi_warps * 4096 * (p->out_lo ? 2 : 1) : 0;
+  int epi_warps = (p->patch && p->gn_ss) ? 4 : 8;
+  auto staging_of = [&](int ew) { return p->tma_store ? ew * 4096 * (p->out_lo ? 2 : 1) : 0; };
+  int nkb_max = 0;
+  for (int c = 0; c < ncls; ++c) nkb_max = p->nkb[c] > nkb_max ? p->nkb[c] : nkb_max;
+  // Eight staging tiles + the statistics scratch leave the BN = 256 layers three 48 KiB stages instead of four (r2: the
+  // 512- and 256-channel VAE convs ran 8-15 % slower than in round 1: 929 -> 1006..1069 us).  Their main loop is >= 16 K
+  // blocks (18 k cycles per tile) and hides a four-warp epilogue, so those layers keep four warps and the fourth stage.
+  if (!p->patch && epi_warps == 8 && nkb_max >= 16 && getenv("GP_EPI_WARPS8") == nullptr &&
+      (kMaxSmem - 3072 - stats_bytes - staging_of(4)) / stage_bytes > (kMaxSmem - 3072 - stats_bytes - staging_of(8)) / stage_bytes)
+    epi_warps = 4;
+  p->epi_warps = epi_warps;
+  const int staging = staging_of(epi_warps);
   // bias: one N tile (288 floats, inside the 3072 reserved bytes) or the whole padded vector when it is small (<= 16 KiB)
   p->bias_slots = kBiasSlots;
   p->bias_all = 0;

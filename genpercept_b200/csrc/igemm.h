@@ -95,6 +95,7 @@ struct IgemmParams {
   int bias_slots;                // floats of shared memory holding the bias: 288 (one N tile, reloaded per tile) or, when the
                                  // layer has several N tiles and Cout is small enough, all of them (loaded once: bias_all)
   int bias_all;
+  int epi_warps;                 // epilogue warps of the tap-streaming kernel: 8, or 4 where 8 would cost a pipeline stage (igemm_finalize)
   int res_prefetch;              // L2-prefetch the next tile's residual boxes one tile period ahead (GP_NO_RES_PREFETCH=1: off)
   CUtensorMap tmRes[kMaxClasses];
   // Patch-resident main loop (igemm_patch.cu; 3x3 stride-1, one source, TW = 128, TH = MT = 1 or 2): per
