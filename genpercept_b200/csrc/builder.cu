@@ -147,7 +147,7 @@ static void choose_tile(int gw, int gh, int rows, int* tw, int* th, int* shift) 
 // Tile shape (BN, MT) for the layers that do not fill the GPU (the UNet's deep levels at any batch, everything at batch
 // 1).  Two bounds per candidate: the tensor time of the longest-running SM — ceil(tiles / SMs) waves of tiles whose
 // duration scales with the MMA width (a 128 x 64 x 16 MMA is bound by its 6 KB of operand fetch: 48 cycles, not 32) — and
-// the L2 -> SM operand traffic, tiles x K x (128 MT + BN) x 2 bytes at 7 TB/s (the d = 512 QK^T sustains 7.4; r2n: the
+// the L2 -> SM operand traffic, tiles x K x (128 MT + BN) x 2 bytes at an effective 7 TB/s (what such few-tile layers sustain; r2n: the
 // 2560 -> 1280 conv on 8 x 12 x 12 pixels moves 796 MB with BN = 256 and 1062 MB with BN = 128: 152 vs 210 us, although
 // BN = 128 doubles the number of busy SMs; at batch 1 the same level has 2 M tiles, BN = 256 keeps 10 SMs busy for 61 us
 // and BN = 64 runs 40 tiles in ~25 us).  A candidate replaces the default only for a predicted gain above 10 %, so
