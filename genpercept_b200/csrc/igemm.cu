@@ -289,6 +289,9 @@ const char* igemm_finalize(IgemmParams* p) {
   if (p->stats && (!p->tma_store || p->Cout > 512 || (p->flags & IG_GEGLU))) return "statistics need the staged epilogue and Cout <= 512";
   // staging: one 4 KiB tile per epilogue warp (8; 4 in the patch kernel's GroupNorm-transform build), x2 for the (hi, lo) layout
   int epi_warps = (p->patch && p->gn_ss) ? 4 : 8;
+  // patch-resident layers without a residual: four warps and the fourth 16 KiB weight-ring stage (see igemm_patch.cu, NE4)
+  if (p->patch && !p->gn_ss && p->tma_store && !p->res_tma && p->res1 == nullptr && p->res2 == nullptr && getenv("GP_PATCH_NE8") == nullptr)
+    epi_warps = 4;
   auto staging_of = [&](int ew) { return p->tma_store ? ew * 4096 * (p->out_lo ? 2 : 1) : 0; };
   int nkb_max = 0;
   for (int c = 0; c < ncls; ++c) nkb_max = p->nkb[c] > nkb_max ? p->nkb[c] : nkb_max;

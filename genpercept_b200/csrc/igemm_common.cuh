@@ -10,7 +10,6 @@
 namespace gp {
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kABytes = kBM * kBK * 2;       // 16 KiB per 128-row tile
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // TMEM columns between the two accumulator buffers

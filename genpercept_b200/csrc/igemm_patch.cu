@@ -61,13 +61,15 @@ __device__ __forceinline__ uint32_t silu_pair_f16(float ha, float hb) {     // i
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-// XFORM = false: no transform warpgroup (256 threads, the full register budget for the epilogue warps — the 384-thread
-// build caps every thread at 168 registers and the TMA-residual epilogue of the short-K layers then runs 20 % slower);
-// the MMA issuers wait for the landed patch directly.  XFORM = true: 384 threads, GroupNorm(+SiLU) in the operand path.
-template <bool BF16, bool XFORM>
+// XFORM = false: no transform warpgroup, eight epilogue warps; the MMA issuers wait for the landed patch directly.
+// XFORM = true: four epilogue warps + the transform warpgroup, GroupNorm(+SiLU) in the operand path.  384 threads either way.
+// NE4 (without XFORM): four epilogue warps, warps 8..11 idle — the layers WITHOUT a residual, where the 16 KiB of staging
+// that eight warps need would cost the fourth weight-ring stage (igemm_finalize): round 1 ran them with 4 warps + 4 stages
+// at 1011-1025 us, eight warps + three stages measured 1053-1195 us (r2v); the residual layers keep eight (1290 -> 1125 us).
+template <bool BF16, bool XFORM, bool NE4>
 __global__ void __launch_bounds__(kPatchThreads, 1) igemm_patch_kernel(const __grid_constant__ IgemmParams p) {
-  // XFORM = false: warps 0..7 epilogue, 8..11 roles.  XFORM = true: warps 0..3 epilogue, 4..7 roles, 8..11 transform.
-  constexpr int NE = XFORM ? 4 : 8;
+  // default: warps 0..7 epilogue, 8..11 roles.  XFORM / NE4: warps 0..3 epilogue, 4..7 roles, 8..11 transform / idle.
+  constexpr int NE = (XFORM || NE4) ? 4 : 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * 128;
@@ -366,8 +368,9 @@ cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t s
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!attr_set[dev]) {
-    const void* fns[4] = {(const void*)igemm_patch_kernel<false, false>, (const void*)igemm_patch_kernel<false, true>,
-                          (const void*)igemm_patch_kernel<true, false>, (const void*)igemm_patch_kernel<true, true>};
+    const void* fns[6] = {(const void*)igemm_patch_kernel<false, false, false>, (const void*)igemm_patch_kernel<false, true, false>,
+                          (const void*)igemm_patch_kernel<true, false, false>,  (const void*)igemm_patch_kernel<true, true, false>,
+                          (const void*)igemm_patch_kernel<false, false, true>,  (const void*)igemm_patch_kernel<true, false, true>};
     for (const void* f : fns) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e != cudaSuccess) return e;
@@ -375,12 +378,15 @@ cudaError_t igemm_patch_launch(const IgemmParams& p_in, int grid, cudaStream_t s
     attr_set[dev] = true;
   }
   const bool xform = p.gn_ss != nullptr;
+  const bool ne4 = !xform && p.epi_warps == 4;
   if (p.flags & IG_BF16) {
-    if (xform) launch(igemm_patch_kernel<true, true>, grid, kPatchThreads, kMaxSmem, stream, p);
-    else launch(igemm_patch_kernel<true, false>, grid, kPatchThreads, kMaxSmem, stream, p);
+    if (xform) launch(igemm_patch_kernel<true, true, false>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else if (ne4) launch(igemm_patch_kernel<true, false, true>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else launch(igemm_patch_kernel<true, false, false>, grid, kPatchThreads, kMaxSmem, stream, p);
   } else {
-    if (xform) launch(igemm_patch_kernel<false, true>, grid, kPatchThreads, kMaxSmem, stream, p);
-    else launch(igemm_patch_kernel<false, false>, grid, kPatchThreads, kMaxSmem, stream, p);
+    if (xform) launch(igemm_patch_kernel<false, true, false>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else if (ne4) launch(igemm_patch_kernel<false, false, true>, grid, kPatchThreads, kMaxSmem, stream, p);
+    else launch(igemm_patch_kernel<false, false, false>, grid, kPatchThreads, kMaxSmem, stream, p);
   }
   return cudaGetLastError();
 }
