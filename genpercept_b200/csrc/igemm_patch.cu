@@ -19,7 +19,8 @@
 // Extra K chunks for a fused 1x1 shortcut (ResnetBlock2D.conv_shortcut over the RAW block input): centre tap only,
 // loaded through a second tensor map and passed through the transform stage untouched.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent).  Default build (XFORM = false): warps 0..7 epilogue (as in igemm.cu),
+// Warp roles (384 threads, 1 CTA / SM, persistent).  Three builds: default (layers with a residual), NE4 (layers without:
+// four epilogue warps, warps 8..11 idle, one more weight-ring stage) and XFORM.  Default (XFORM = false): warps 0..7 epilogue (as in igemm.cu),
 // warp 8 patch producer (TMA), warps 9 (,10) MMA issuers — one per image row of the tile (MT = TH = 1 or 2), warp 10 also
 // owns the TMEM allocation —, warp 11 weight producer (one TMA box per (chunk, tap)).  GroupNorm-transform build
 // (XFORM = true, GP_GN_FUSE=1): warps 0..3 epilogue, 4..7 the same roles, 8..11 operand transform (GroupNorm scale/shift +
