@@ -176,6 +176,24 @@ static TileShape choose_tile_shape(int cout, double k_elems, int num_sms, TileSh
     }
   return best;
 }
+// Default (choose_bn, two M tiles when the N tile is narrow and the layer fills the GPU) + the model above, for a stride-1
+// layer of `images` maps of gw x gh output pixels (tokens_mode: one row of images * gw * gh tokens).  Host-only; exported
+// as gp_tile_shape so that the decision table is pinned by a CPU test.
+void tile_shape_for(int cout, double k_elems, bool tokens_mode, int images, int gw, int gh, int num_sms, int* bn, int* mt) {
+  const long long work_px = (long long)images * gw * gh;
+  const int bn0 = choose_bn(cout, 0);
+  const int mt0 = (bn0 <= 128 && work_px >= 256LL * 148) ? 2 : 1;
+  auto mtiles_of = [&](int m) -> long long {
+    if (tokens_mode) return (work_px + 128 * m - 1) / (128 * m);
+    int tw = 128, th = m, sh = 7;
+    choose_tile(gw, gh, 128 * m, &tw, &th, &sh);
+    return (long long)images * ceil_div(gw, tw) * ceil_div(gh, th);
+  };
+  const TileShape ts = choose_tile_shape(cout, k_elems, num_sms, TileShape{bn0, mt0}, mtiles_of);
+  *bn = ts.bn;
+  *mt = ts.mt;
+}
+
 static void check_cuda(cudaError_t e, const std::string& what) {
   if (e != cudaSuccess) throw GpError(GP_ERR_CUDA, what + ": " + cudaGetErrorString(e));
 }
@@ -245,17 +263,9 @@ void Builder::conv(const std::string& name, const ConvArgs& a) {
   int bn_pre = choose_bn(Cout, a.force_bn);
   int mt_pre = gn_fused ? ((bn_pre <= 128 && (H % 2) == 0) ? 2 : 1) : (bn_pre <= 128 && work_px >= 256LL * 148) ? 2 : 1;
   if (!a.force_bn && !(a.flags & IG_GEGLU) && !gn_fused) {
-    const int gw = (a.mode == 3) ? W : Wo, gh = (a.mode == 3) ? H : Ho;
-    auto mtiles_of = [&](int mt) -> long long {
-      if (tokens_mode) return (work_px + 128 * mt - 1) / (128 * mt);
-      int tw = 128, th = mt, sh = 7;
-      choose_tile(gw, gh, 128 * mt, &tw, &th, &sh);
-      return (long long)N * (a.mode == 3 ? 4 : 1) * ceil_div(gw, tw) * ceil_div(gh, th);
-    };
     const double k_elems = flops / (2.0 * N * Ho * Wo * (double)Cout) * (a.mode == 3 ? 4.0 / 9.0 : 1.0);
-    const TileShape ts = choose_tile_shape(Cout, k_elems, num_sms, TileShape{bn_pre, mt_pre}, mtiles_of);
-    bn_pre = ts.bn;
-    mt_pre = ts.mt;
+    tile_shape_for(Cout, k_elems, tokens_mode, N * (a.mode == 3 ? 4 : 1), (a.mode == 3) ? W : Wo, (a.mode == 3) ? H : Ho, num_sms,
+                   &bn_pre, &mt_pre);
   }
   const bool is_geglu = (a.flags & IG_GEGLU) != 0;
   const bool staged = !a.out_f32 && std::getenv("GP_DIRECT_EPILOGUE") == nullptr &&

@@ -1233,6 +1233,12 @@ gp_status gp_plan(gp_engine* e, int B, int H, int W) {
 
 int gp_plan_count(gp_engine* e) { return e ? (int)e->plans.size() : 0; }
 
+gp_status gp_tile_shape(int cout, int cin, int ks, int images, int h, int w, int tokens_mode, int num_sms, int* bn, int* mt) {
+  if (!bn || !mt || cout < 1 || cin < 1 || ks < 1 || images < 1 || h < 1 || w < 1 || num_sms < 1) return GP_ERR_INVALID;
+  gp::tile_shape_for(cout, (double)cin * ks * ks, tokens_mode != 0, images, w, h, num_sms, bn, mt);
+  return GP_OK;
+}
+
 static void set_timestep_now(gp_engine* e, int timestep);
 
 gp_status gp_set_timestep(gp_engine* e, int timestep) {

@@ -167,4 +167,7 @@ class Builder {
   Arena arena_;
 };
 
+// builder.cu: (BN, MT) of a stride-1 implicit-GEMM layer (default policy + the waves / L2-traffic model)
+void tile_shape_for(int cout, double k_elems, bool tokens_mode, int images, int gw, int gh, int num_sms, int* bn, int* mt);
+
 }  // namespace gp

@@ -56,6 +56,7 @@ def lib():
                                  c_int, c_int, c_void_p]
     L.gp_ensemble_reduce.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.gp_plan_count.argtypes = [c_void_p]
+    L.gp_tile_shape.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
     L.gp_tensor_shape.argtypes = [c_void_p, c_char_p, POINTER(c_int64)]
     L.gp_read_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
     L.gp_write_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_size_t]
@@ -427,6 +428,14 @@ def quantize(pred, bits=16, to_host=True):
                            _stream_ptr())
     _check_free(st, "gp_quantize")
     return out
+
+
+def tile_shape(cout, cin, ks, images, h, w, tokens_mode=False, num_sms=148):
+    """(BN, MT) the planner gives a stride-1 layer (host-only, DESIGN.md section 4 "Tile shape per layer")."""
+    bn, mt = c_int(), c_int()
+    st = lib().gp_tile_shape(cout, cin, ks, images, h, w, 1 if tokens_mode else 0, num_sms, byref(bn), byref(mt))
+    _check_free(st, "gp_tile_shape")
+    return bn.value, mt.value
 
 
 def bench_conv(dtype, N, H, W, Cin, Cout, ks=3, mode=0, iters=10):

@@ -77,6 +77,11 @@ gp_status gp_plan(gp_engine* e, int batch, int height, int width);
 
 /* number of cached plans (the cache is bounded: least-recently-used plans are destroyed; GP_MAX_PLANS, default 4) */
 int gp_plan_count(gp_engine* e);
+/* Host-only introspection (no device needed): the N tile (BN) and the number of 128-pixel M tiles per CTA (MT) the planner
+ * gives a stride-1 ks x ks convolution / linear layer cin -> cout over `images` maps of h x w output pixels on a GPU with
+ * num_sms SMs (tokens_mode != 0: one row of images * h * w tokens).  Nothing in the reference corresponds to it (PyTorch /
+ * cuDNN pick their own tiles); it pins the tile policy of DESIGN.md section 4 in the CPU tests. */
+gp_status gp_tile_shape(int cout, int cin, int ks, int images, int h, int w, int tokens_mode, int num_sms, int* bn, int* mt);
 /* replaces: the per-call `fix_timesteps` of single_infer (/root/reference/genpercept/genpercept_pipeline.py:405-408).
  * The timestep only enters through conv1.bias + time_emb_proj(silu(emb(t))) of the 22 UNet ResNets; those biases are
  * re-folded on the host (cached per timestep) and rewritten in place after a device synchronisation. */
